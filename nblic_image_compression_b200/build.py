@@ -1,0 +1,60 @@
+"""Builds libnblic_b200.so in-tree (nvcc cross-compiles sm_100a without a GPU).
+
+The shared library is the product: CUDA kernels + batch C ABI (csrc/stream_kernels.cu) and the
+reference codec's five drop-in entry points in C (csrc/nblic_dropin.c).  It is git-ignored but
+travels to the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libnblic_b200.so")
+SOURCES_CU = ["stream_kernels.cu"]
+SOURCES_C = ["nblic_dropin.c"]
+HEADERS = [os.path.join(CSRC, "codec_core.cuh"), os.path.join(HERE, "..", "include", "nblic_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--fmad=false"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.sep not in cand or os.path.exists(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, s) for s in SOURCES_CU + SOURCES_C]
+    if not force and not _stale(LIB, srcs + HEADERS + [os.path.abspath(__file__)]):
+        return LIB
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for s in SOURCES_CU:
+        o = os.path.join(objdir, s + ".o")
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.run(cmd, check=True)
+        objs.append(o)
+    for s in SOURCES_C:
+        o = os.path.join(objdir, s + ".o")
+        subprocess.run(["gcc", "-O2", "-fPIC", "-Wall", "-Wextra", "-std=gnu99", "-c", os.path.join(CSRC, s), "-o", o], check=True)
+        objs.append(o)
+    subprocess.run([_nvcc(), "-shared", "-o", LIB, *objs, "-lpthread", "-cudart", "shared"], check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

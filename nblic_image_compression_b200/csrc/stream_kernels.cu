@@ -1,0 +1,703 @@
+/*
+ * stream_kernels.cu -- the sm_100a kernels and the batch C ABI of libnblic_b200.so.
+ *
+ * Kernels
+ *   coder_kernel<KIND, DEC, MAP>   one coder stream (= one image) per warp (MAP_WARP: adaptive state in
+ *                                  shared memory) or per lane (MAP_LANE: state in L2/HBM); a persistent
+ *                                  grid pulls images from an atomic queue, largest first.
+ *   scan_lengths_kernel            exclusive scan of the per-image stream lengths (warp shuffles).
+ *   gather_streams_kernel          packs the variable-length streams (and joins QNBLIC's head with
+ *                                  its downward-written rANS tail) into one contiguous buffer.
+ *   peek_headers_kernel            header fields of device-resident streams.
+ *   synth_gray_kernel              the deterministic test-image generator.
+ *
+ * Host side: nblic_b200_* (include/nblic_b200.h).  No CPU fallback anywhere: without a usable CUDA
+ * device every entry point fails.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/nblic_b200.h"
+#include "codec_core.cuh"
+
+using namespace nblic;
+
+namespace {
+
+enum { KIND_Q = 0, KIND_N = 1 };
+enum { MAP_WARP = 1, MAP_LANE = 2 };
+
+/* one entry per image of the batch, device resident */
+struct Task {
+    const uint8_t *src;  /* pixels in (encode)                                   */
+    uint8_t *rec;        /* reconstruction (near > 0 encode) / decoded raster    */
+    uint8_t *slot;       /* encode: private worst-case output slot; decode: stream bytes */
+    uint8_t *sym;        /* QNBLIC encode scratch (2 B / pixel)                   */
+    u32 slot_cap;        /* bytes (encode: capacity, decode: valid)               */
+    u32 head_len;        /* out: bytes at the start of the slot                   */
+    u32 tail_len;        /* out: bytes at the end of the slot (QNBLIC rANS words) */
+    int status;          /* out                                                   */
+    int h, w, near, k_step, effort;
+};
+
+constexpr int N_STATE_BYTES = N_CTX_ENTRIES * 2 + N_FOREST_ENTRIES * 4 + N_RANK_ENTRIES * 2 + N_RANK_ENTRIES * 4; /* 81920 */
+constexpr int N_SMEM_BYTES = N_CTX_ENTRIES * 2 + N_FOREST_ENTRIES * 4 + N_RANK_ENTRIES * 2;                       /* 40960 */
+constexpr int N_COUNT_BYTES = N_RANK_ENTRIES * 4;
+constexpr int Q_STATE_BYTES = Q_CTX_ENTRIES * 4 + Q_TAB_ENTRIES * 4; /* 24576 */
+
+__device__ __forceinline__ NState carve_nstate(uint8_t *hot, uint8_t *counts, i64 *avp, size_t avp_half) {
+    NState s;
+    s.forest = reinterpret_cast<u32 *>(hot);
+    s.ctx = reinterpret_cast<int16_t *>(hot + N_FOREST_ENTRIES * 4);
+    s.rank_of = hot + N_FOREST_ENTRIES * 4 + N_CTX_ENTRIES * 2;
+    s.sym_at = s.rank_of + N_RANK_ENTRIES;
+    s.count = reinterpret_cast<int *>(counts);
+    s.Brow = avp;
+    s.Frow = avp ? avp + avp_half : nullptr;
+    return s;
+}
+
+template <bool DEC>
+__device__ void run_nblic(Task &t, const NState &st, int lane, int nl) {
+    nstate_reset(st, lane, nl);
+    const int n = t.effort == 1 ? 0 : (t.effort == 2 ? 6 : 10);
+    if (n > 0) {
+        const size_t cells = (size_t)t.w * (1 + n + n * n);
+        for (size_t k = lane; k < cells; k += nl) st.Brow[k] = 0;
+    }
+    if (nl > 1) __syncwarp();
+    if (lane == 0) {
+        NJob job;
+        job.src = t.src; job.rec = t.rec; job.stream = t.slot; job.stream_cap = t.slot_cap;
+        job.h = t.h; job.w = t.w; job.near = t.near; job.k_step = t.k_step;
+        u32 len;
+        if (n == 0) len = nblic_stream<0, DEC>(job, st);
+        else if (n == 6) len = nblic_stream<6, DEC>(job, st);
+        else len = nblic_stream<10, DEC>(job, st);
+        if (!DEC) {
+            if (len == 0xffffffffu) { t.status = NBLIC_B200_OVERFLOW; t.head_len = 0; }
+            else t.head_len = len;
+            t.tail_len = 0;
+        }
+    }
+    if (nl > 1) __syncwarp();
+}
+
+template <bool DEC>
+__device__ void run_qnblic(Task &t, const QState &st, int lane, int nl) {
+    if (nl > 1) __syncwarp();
+    if (lane == 0) {
+        QJob job;
+        job.src = t.src; job.rec = t.rec; job.stream = reinterpret_cast<uint16_t *>(t.slot);
+        job.stream_cap_words = t.slot_cap / 2; job.sym = t.sym; job.h = t.h; job.w = t.w;
+        if (DEC) qnblic_decode_stream(job, st);
+        else {
+            u32 head = 0, tail = 0;
+            if (qnblic_encode_stream(job, st, head, tail)) { t.head_len = head * 2; t.tail_len = tail * 2; }
+            else { t.status = NBLIC_B200_OVERFLOW; t.head_len = t.tail_len = 0; }
+        }
+    }
+    if (nl > 1) __syncwarp();
+}
+
+/*
+ * Persistent coder kernel.  `order` lists the task indices of this launch, largest image first;
+ * `queue` is the shared cursor.  MAP_WARP: blockDim = 32, dynamic shared memory holds the hot
+ * adaptive state of the warp's current stream; `cold` holds per-slot state that does not fit
+ * (rank-mapper frequencies).  MAP_LANE: every thread is a slot and all state is in `cold`.
+ */
+template <int KIND, bool DEC, int MAP>
+__global__ void __launch_bounds__(32) coder_kernel(Task *tasks, const int *order, int n_order, int *queue, uint8_t *cold,
+                                                   size_t cold_stride, i64 *avp, size_t avp_stride) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const size_t slot = MAP == MAP_WARP ? blockIdx.x : (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t *my_cold = cold + slot * cold_stride;
+    i64 *my_avp = avp ? avp + slot * avp_stride : nullptr;
+    for (;;) {
+        int pos;
+        if (MAP == MAP_WARP) {
+            pos = lane == 0 ? atomicAdd(queue, 1) : 0;
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+        } else {
+            pos = atomicAdd(queue, 1);
+        }
+        if (pos >= n_order) break;
+        Task &t = tasks[order[pos]];
+        if (KIND == KIND_N) {
+            const NState st = MAP == MAP_WARP ? carve_nstate(smem, my_cold, my_avp, avp_stride / 2)
+                                              : carve_nstate(my_cold, my_cold + N_SMEM_BYTES, my_avp, avp_stride / 2);
+            run_nblic<DEC>(t, st, MAP == MAP_WARP ? lane : 0, MAP == MAP_WARP ? 32 : 1);
+        } else {
+            QState st;
+            uint8_t *base = MAP == MAP_WARP ? smem : my_cold;
+            st.ctx = reinterpret_cast<int *>(base);
+            st.tab = reinterpret_cast<u32 *>(base + Q_CTX_ENTRIES * 4);
+            run_qnblic<DEC>(t, st, MAP == MAP_WARP ? lane : 0, MAP == MAP_WARP ? 32 : 1);
+        }
+    }
+}
+
+/* Exclusive scan of head_len + tail_len over the batch; one CTA of 1024 threads, warp shuffles. */
+__global__ void __launch_bounds__(1024) scan_lengths_kernel(const Task *tasks, int n, unsigned long long *offsets) {
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long len = i < n ? (unsigned long long)tasks[i].head_len + tasks[i].tail_len : 0ull;
+        unsigned long long v = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
+        if (lane == 31) warp_sum[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long s = warp_sum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += o; }
+            warp_sum[lane] = s;
+        }
+        __syncthreads();
+        const unsigned long long before = carry + (wid ? warp_sum[wid - 1] : 0ull) + v - len;
+        if (i < n) offsets[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + len;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+/* Pack the streams: CTA (chunk, image) copies up to `chunk` bytes of image's stream.  The head comes
+ * from the start of the slot, the tail from its end. */
+__global__ void __launch_bounds__(256) gather_streams_kernel(const Task *tasks, const unsigned long long *offsets, uint8_t *out,
+                                                             unsigned long long out_cap, u32 chunk, int *overflow) {
+    const Task &t = tasks[blockIdx.y];
+    const u32 total = t.head_len + t.tail_len;
+    const u32 begin = blockIdx.x * chunk;
+    if (begin >= total) return;
+    const u32 end = min(total, begin + chunk);
+    const unsigned long long dst0 = offsets[blockIdx.y];
+    if (dst0 + total > out_cap) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(overflow, 1); return; }
+    const uint8_t *tail = t.slot + (t.slot_cap & ~1u) - t.tail_len;
+    for (u32 k = begin + threadIdx.x; k < end; k += blockDim.x)
+        out[dst0 + k] = k < t.head_len ? t.slot[k] : tail[k - t.head_len];
+}
+
+struct Peek { int h, w, near, k_step, effort, ok; };
+
+__host__ __device__ inline Peek peek_bytes(const uint8_t *p, size_t len) { /* R: NBLIC.c:698-745, QNBLIC.c:475-486 */
+    Peek r = {0, 0, 0, 0, 0, 0};
+    if (len >= 8 && p[0] == 0x51 && p[1] == 0x30 && p[2] == 0x2e && p[3] == 0x32) { /* "Q0.2" as LE words */
+        r.h = p[4] | (p[5] << 8); r.w = p[6] | (p[7] << 8); r.effort = 0;
+        r.ok = r.h > 0 && r.w > 0 && (long long)r.h * r.w <= 100000000LL;
+        return r;
+    }
+    const char magic[9] = "NBLIC0.3";
+    if (len < 16) return r;
+    for (int k = 0; k < 8; k++) if (p[k] != (uint8_t)magic[k]) return r;
+    const int channels = p[8];
+    r.h = (p[9] << 8) | p[10]; r.w = (p[11] << 8) | p[12]; r.near = p[13]; r.k_step = p[14]; r.effort = p[15];
+    r.ok = r.h > 0 && r.w > 0 && (long long)r.h * r.w <= 100000000LL && channels <= 1 && r.near <= 9 && r.k_step >= 3 && r.k_step <= 16 &&
+           r.effort >= 1 && r.effort <= 3;
+    return r;
+}
+
+__global__ void peek_headers_kernel(const uint8_t *streams, const unsigned long long *starts, const unsigned long long *lens, int n, Peek *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = peek_bytes(streams + starts[i], (size_t)lens[i]);
+}
+
+/* ---- synthetic photographic-like generator (nblic_image_compression_b200/synth.py) ---- */
+__device__ __forceinline__ u32 h32(u32 v) { v ^= v >> 16; v *= 0x7feb352du; v ^= v >> 15; v *= 0x846ca68bu; v ^= v >> 16; return v; }
+__device__ __forceinline__ int lattice(u32 key, int ix, int iy) { return (int)(h32(((u32)ix * 0x9E3779B1u) ^ h32(((u32)iy * 0x85EBCA77u) ^ key)) & 255u); }
+
+struct Occluders { int v[12][5]; };
+
+__global__ void __launch_bounds__(256) synth_gray_kernel(uint8_t *out, int h, int w, u32 seed, Occluders occ) {
+    const long long n = (long long)h * w;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(p / w), x = (int)(p % w);
+        const int shifts[7] = {8, 7, 6, 5, 4, 3, 2}, amps[7] = {64, 48, 32, 20, 12, 7, 4};
+        int acc = 0;
+#pragma unroll
+        for (int o = 0; o < 7; o++) {
+            const int sh = shifts[o], S = 1 << sh;
+            const u32 key = seed * 131u + (u32)o * 7919u;
+            const int ix = x >> sh, iy = y >> sh, fx = x & (S - 1), fy = y & (S - 1);
+            const int v00 = lattice(key, ix, iy), v10 = lattice(key, ix + 1, iy), v01 = lattice(key, ix, iy + 1), v11 = lattice(key, ix + 1, iy + 1);
+            const int v = ((v00 * (S - fx) + v10 * fx) * (S - fy) + (v01 * (S - fx) + v11 * fx) * fy) >> (2 * sh);
+            acc += amps[o] * v;
+        }
+        int img = acc / 187;
+        img = 128 + (((img - 128) * 3) >> 1);
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            const long long dx = x - occ.v[k][0], dy = y - occ.v[k][1], rad = occ.v[k][2];
+            const bool in = occ.v[k][4] == 0 ? (dx * dx + dy * dy < rad * rad) : ((dx < 0 ? -dx : dx) < rad && (dy < 0 ? -dy : dy) < rad / 2 + 1);
+            if (in) img += occ.v[k][3];
+        }
+        const u32 hn = h32(((u32)x * 0x27d4eb2du) ^ h32((u32)y ^ (seed * 977u + 12345u)));
+        const int nz = (int)((hn & 3) + ((hn >> 4) & 3) + ((hn >> 8) & 3) + ((hn >> 12) & 3)) - 6;
+        out[p] = (uint8_t)min(max(img + nz, 0), 255);
+    }
+}
+
+/* ---- host-side helpers ----------------------------------------------------------------------- */
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+std::string g_create_error;
+
+} /* namespace */
+
+struct nblic_b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int mapping = NBLIC_B200_MAP_AUTO;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+    float coder_ms = 0.f;
+    const char *last_map = "none";
+    DevBuf tasks, order, queue, slots, sym, cold, avp, offsets, flags, pixels, streams, recon, peeks;
+    int occ_warp[2] = {0, 0};
+};
+
+namespace {
+
+bool fail(nblic_b200_ctx *c, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->error = buf; else g_create_error = buf;
+    return false;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return -1; } } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct LaunchPlan { int map; int grid; size_t cold_stride; size_t smem; };
+
+template <int KIND, bool DEC, int MAP>
+int launch_coder_t(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, const LaunchPlan &plan, size_t avp_stride) {
+    auto kern = coder_kernel<KIND, DEC, MAP>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    kern<<<plan.grid, 32, plan.smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (uint8_t *)c->cold.p, plan.cold_stride,
+                                                   avp_stride ? (i64 *)c->avp.p : nullptr, avp_stride);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int KIND, bool DEC>
+int launch_coder(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w, int max_effort) {
+    int map = c->mapping;
+    if (map == NBLIC_B200_MAP_AUTO) map = MAP_WARP;
+    LaunchPlan plan;
+    plan.map = map;
+    if (map == MAP_WARP) {
+        plan.smem = KIND == KIND_N ? N_SMEM_BYTES : Q_STATE_BYTES;
+        plan.cold_stride = KIND == KIND_N ? N_COUNT_BYTES : 0;
+        int per_sm = 0;
+        auto kern = coder_kernel<KIND, DEC, MAP_WARP>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, plan.smem));
+        plan.grid = std::min(n_order, c->sm_count * std::max(per_sm, 1));
+    } else {
+        plan.smem = 0;
+        plan.cold_stride = KIND == KIND_N ? N_STATE_BYTES : Q_STATE_BYTES;
+        const int lanes = std::min(n_order, c->sm_count * 32 * 8);
+        plan.grid = (lanes + 31) / 32;
+    }
+    size_t avp_stride = 0;
+    if (KIND == KIND_N && max_effort >= 2) { /* AVP column accumulators: bound the slot count by a 24 GB budget */
+        const int n = max_effort == 2 ? 6 : 10;
+        avp_stride = 2 * (size_t)max_w * (1 + n + n * n);
+        const size_t budget_slots = std::max<size_t>(((size_t)24 << 30) / (avp_stride * sizeof(i64)), 1);
+        if (map == MAP_WARP) plan.grid = (int)std::min<size_t>((size_t)plan.grid, budget_slots);
+        else plan.grid = (int)std::max<size_t>(std::min<size_t>((size_t)plan.grid, budget_slots / 32), 1);
+    }
+    const size_t slots = map == MAP_WARP ? (size_t)plan.grid : (size_t)plan.grid * 32;
+    CK(c->cold.reserve(std::max<size_t>(slots * plan.cold_stride, 16)));
+    if (avp_stride) CK(c->avp.reserve(slots * avp_stride * sizeof(i64)));
+    c->last_map = map == MAP_WARP ? "warp" : "lane";
+    if (map == MAP_WARP) return launch_coder_t<KIND, DEC, MAP_WARP>(c, n_order, d_order, d_queue, plan, avp_stride);
+    return launch_coder_t<KIND, DEC, MAP_LANE>(c, n_order, d_order, d_queue, plan, avp_stride);
+}
+
+/* Upload tasks, run the coder kernels for the Q and N groups, download the task results. */
+template <bool DEC>
+int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
+    const int n = (int)tasks.size();
+    std::vector<int> order_q, order_n;
+    int max_w = 1, max_effort = 0;
+    for (int i = 0; i < n; i++) {
+        if (tasks[i].status != NBLIC_B200_OK) continue;
+        (tasks[i].effort == 0 ? order_q : order_n).push_back(i);
+        if (tasks[i].effort > 0) { max_w = std::max(max_w, tasks[i].w); max_effort = std::max(max_effort, tasks[i].effort); }
+    }
+    auto by_size = [&](int a, int b) {
+        const long long pa = (long long)tasks[a].h * tasks[a].w, pb = (long long)tasks[b].h * tasks[b].w;
+        return pa != pb ? pa > pb : a < b;
+    };
+    std::sort(order_q.begin(), order_q.end(), by_size);
+    std::sort(order_n.begin(), order_n.end(), by_size);
+
+    CK(c->tasks.reserve(sizeof(Task) * (size_t)std::max(n, 1)));
+    CK(c->order.reserve(sizeof(int) * (size_t)std::max(n, 1)));
+    CK(c->queue.reserve(2 * sizeof(int)));
+    CK(cudaMemcpyAsync(c->tasks.p, tasks.data(), sizeof(Task) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    std::vector<int> order(order_q);
+    order.insert(order.end(), order_n.begin(), order_n.end());
+    if (!order.empty()) CK(cudaMemcpyAsync(c->order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->queue.p, 0, 2 * sizeof(int), c->stream));
+
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (!order_q.empty()) {
+        if (launch_coder<KIND_Q, DEC>(c, (int)order_q.size(), (const int *)c->order.p, (int *)c->queue.p, 1, 0)) return -1;
+    }
+    if (!order_n.empty()) {
+        if (launch_coder<KIND_N, DEC>(c, (int)order_n.size(), (const int *)c->order.p + order_q.size(), (int *)c->queue.p + 1, max_w, max_effort)) return -1;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    return 0;
+}
+
+int finish_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
+    CK(cudaMemcpyAsync(tasks.data(), c->tasks.p, sizeof(Task) * tasks.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->coder_ms, c->ev0, c->ev1));
+    return 0;
+}
+
+void resolve_mode(int near, int effort, int &near_out, int &effort_out) { /* R: NBLIC_main.c:182-189, NBLIC.c:768-770 */
+    if (near == 0 && effort == 0) { near_out = 0; effort_out = 0; return; }
+    near_out = std::min(std::max(near, 0), 9);
+    effort_out = std::min(std::max(effort, 1), 3);
+}
+
+} /* namespace */
+
+/* ============================================================================================ */
+/* C ABI                                                                                        */
+/* ============================================================================================ */
+
+extern "C" {
+
+const char *nblic_b200_version(void) { return "nblic_b200 0.1 (sm_100a)"; }
+
+size_t nblic_b200_stream_bound(int height, int width) {
+    if (height <= 0 || width <= 0) return 8192;
+    return 2 * (size_t)height * (size_t)width + 8192;
+}
+
+nblic_b200_ctx *nblic_b200_create(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) { fail(nullptr, "no CUDA device: %s", cudaGetErrorString(e)); return nullptr; }
+    if (device < 0 || device >= count) { fail(nullptr, "device %d out of range (have %d)", device, count); return nullptr; }
+    nblic_b200_ctx *c = new (std::nothrow) nblic_b200_ctx;
+    if (!c) return nullptr;
+    c->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreate(&c->ev0)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+        fail(nullptr, "device %d setup failed: %s", device, cudaGetErrorString(e));
+        delete c;
+        return nullptr;
+    }
+    if (prop.major < 10) { fail(nullptr, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor); delete c; return nullptr; }
+    c->sm_count = prop.multiProcessorCount;
+    return c;
+}
+
+void nblic_b200_destroy(nblic_b200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->tasks, &c->order, &c->queue, &c->slots, &c->sym, &c->cold, &c->avp, &c->offsets, &c->flags, &c->pixels, &c->streams, &c->recon, &c->peeks};
+    for (DevBuf *b : bufs) b->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *nblic_b200_last_error(const nblic_b200_ctx *c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+
+int nblic_b200_set_mapping(nblic_b200_ctx *c, int mapping) {
+    if (!c || mapping < NBLIC_B200_MAP_AUTO || mapping > NBLIC_B200_MAP_LANE) return -1;
+    c->mapping = mapping;
+    return 0;
+}
+
+uint64_t nblic_b200_launch_count(const nblic_b200_ctx *c) { return c ? c->launches : 0; }
+float nblic_b200_last_coder_ms(const nblic_b200_ctx *c) { return c ? c->coder_ms : 0.f; }
+const char *nblic_b200_last_mapping(const nblic_b200_ctx *c) { return c ? c->last_map : "none"; }
+
+int nblic_b200_peek(const uint8_t *stream, size_t len, int *height, int *width, int *near, int *effort) {
+    if (!stream) return -1;
+    const Peek p = peek_bytes(stream, len);
+    if (height) *height = p.h;
+    if (width) *width = p.w;
+    if (near) *near = p.near;
+    if (effort) *effort = p.effort;
+    return p.ok ? 0 : -1;
+}
+
+int nblic_b200_encode_batch_device(nblic_b200_ctx *c, int n, const uint8_t *d_pixels, const uint64_t *pix_off, const int *heights,
+                                   const int *widths, int near, int effort, uint8_t *d_streams, uint64_t stream_cap,
+                                   uint64_t *stream_off, uint8_t *d_recon, int *status) {
+    if (!c) return -1;
+    if (n < 0 || (n > 0 && (!d_pixels || !pix_off || !heights || !widths || !d_streams || !stream_off))) { fail(c, "bad arguments"); return -1; }
+    CK(cudaSetDevice(c->device));
+    int near_c, effort_c;
+    resolve_mode(near, effort, near_c, effort_c);
+    if (n == 0) { if (stream_off) stream_off[0] = 0; return 0; }
+
+    std::vector<Task> tasks((size_t)n);
+    size_t slot_total = 0, sym_total = 0, recon_total = 0;
+    for (int i = 0; i < n; i++) {
+        Task &t = tasks[(size_t)i];
+        memset(&t, 0, sizeof t);
+        t.h = heights[i]; t.w = widths[i]; t.near = near_c; t.effort = effort_c;
+        t.k_step = std::min(std::max(3 + 2 * near_c, 3), 16);
+        const bool ok = t.h > 0 && t.w > 0 && t.h <= 65535 && t.w <= 65535 && (long long)t.h * t.w <= 100000000LL;
+        t.status = ok ? NBLIC_B200_OK : NBLIC_B200_BAD_DIMS;
+        if (!ok) continue;
+        const size_t px = (size_t)t.h * t.w;
+        t.slot_cap = (u32)std::min<size_t>(nblic_b200_stream_bound(t.h, t.w), 0xfffffff0u);
+        slot_total += align_up(t.slot_cap, 256);
+        if (effort_c == 0) sym_total += align_up(2 * px, 256);
+        if (near_c > 0 && !d_recon) recon_total += align_up(px, 256);
+    }
+    CK(c->slots.reserve(std::max<size_t>(slot_total, 16)));
+    CK(c->sym.reserve(std::max<size_t>(sym_total, 16)));
+    CK(c->recon.reserve(std::max<size_t>(recon_total, 16)));
+    size_t slot_at = 0, sym_at = 0, recon_at = 0;
+    for (int i = 0; i < n; i++) {
+        Task &t = tasks[(size_t)i];
+        if (t.status != NBLIC_B200_OK) continue;
+        const size_t px = (size_t)t.h * t.w;
+        t.src = d_pixels + pix_off[i];
+        t.slot = (uint8_t *)c->slots.p + slot_at; slot_at += align_up(t.slot_cap, 256);
+        if (effort_c == 0) { t.sym = (uint8_t *)c->sym.p + sym_at; sym_at += align_up(2 * px, 256); }
+        if (near_c > 0) {
+            if (d_recon) t.rec = d_recon + pix_off[i];
+            else { t.rec = (uint8_t *)c->recon.p + recon_at; recon_at += align_up(px, 256); }
+        }
+    }
+    if (run_tasks<false>(c, tasks)) return -1;
+
+    /* compaction: exclusive scan of the lengths, then a coalesced gather */
+    CK(c->offsets.reserve(sizeof(unsigned long long) * ((size_t)n + 1)));
+    CK(c->flags.reserve(sizeof(int)));
+    CK(cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream));
+    scan_lengths_kernel<<<1, 1024, 0, c->stream>>>((const Task *)c->tasks.p, n, (unsigned long long *)c->offsets.p);
+    c->launches++;
+    u32 max_cap = 0;
+    for (const Task &t : tasks) max_cap = std::max(max_cap, t.slot_cap);
+    const u32 chunk = 16384;
+    dim3 grid((max_cap + chunk - 1) / chunk, (unsigned)n);
+    gather_streams_kernel<<<grid, 256, 0, c->stream>>>((const Task *)c->tasks.p, (const unsigned long long *)c->offsets.p, d_streams,
+                                                        stream_cap, chunk, (int *)c->flags.p);
+    c->launches++;
+    CK(cudaGetLastError());
+    int overflow = 0;
+    CK(cudaMemcpyAsync(stream_off, c->offsets.p, sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&overflow, c->flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (finish_tasks(c, tasks)) return -1;
+    int failed = 0;
+    for (int i = 0; i < n; i++) {
+        int st = tasks[(size_t)i].status;
+        if (st == NBLIC_B200_OK && overflow && stream_off[i + 1] > stream_cap) st = NBLIC_B200_OVERFLOW;
+        if (status) status[i] = st;
+        failed += st != NBLIC_B200_OK;
+    }
+    return failed;
+}
+
+/* starts[i], lens[i]: extent of stream i inside d_streams */
+int decode_device_impl(nblic_b200_ctx *c, int n, const uint8_t *d_streams, const uint64_t *starts, const uint64_t *lens,
+                              uint8_t *d_pixels, const uint64_t *pix_off, int *status) {
+    /* header fields of every stream, gathered on the device */
+    CK(c->offsets.reserve(sizeof(unsigned long long) * 2 * (size_t)n));
+    CK(c->peeks.reserve(sizeof(Peek) * (size_t)n));
+    unsigned long long *d_starts = (unsigned long long *)c->offsets.p, *d_lens = d_starts + n;
+    CK(cudaMemcpyAsync(d_starts, starts, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_lens, lens, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    peek_headers_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(d_streams, d_starts, d_lens, n, (Peek *)c->peeks.p);
+    c->launches++;
+    std::vector<Peek> peeks((size_t)n);
+    CK(cudaMemcpyAsync(peeks.data(), c->peeks.p, sizeof(Peek) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+
+    std::vector<Task> tasks((size_t)n);
+    for (int i = 0; i < n; i++) {
+        Task &t = tasks[(size_t)i];
+        memset(&t, 0, sizeof t);
+        const Peek &p = peeks[(size_t)i];
+        t.h = p.h; t.w = p.w; t.near = p.near; t.k_step = p.k_step; t.effort = p.effort;
+        t.status = p.ok ? NBLIC_B200_OK : NBLIC_B200_BAD_HEADER;
+        t.slot = const_cast<uint8_t *>(d_streams) + starts[i];
+        t.slot_cap = (u32)std::min<uint64_t>(lens[i], 0xfffffff0u);
+        t.rec = d_pixels + pix_off[i];
+        if (p.ok && p.effort == 0 && ((uintptr_t)t.slot & 1)) t.status = NBLIC_B200_BAD_HEADER; /* QNBLIC words must be 2-byte aligned */
+    }
+    if (run_tasks<true>(c, tasks)) return -1;
+    if (finish_tasks(c, tasks)) return -1;
+    int failed = 0;
+    for (int i = 0; i < n; i++) { if (status) status[i] = tasks[(size_t)i].status; failed += tasks[(size_t)i].status != NBLIC_B200_OK; }
+    return failed;
+}
+
+int nblic_b200_decode_batch_device(nblic_b200_ctx *c, int n, const uint8_t *d_streams, const uint64_t *stream_off, uint8_t *d_pixels,
+                                   const uint64_t *pix_off, int *status) {
+    if (!c) return -1;
+    if (n < 0 || (n > 0 && (!d_streams || !stream_off || !d_pixels || !pix_off))) { fail(c, "bad arguments"); return -1; }
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return 0;
+    std::vector<uint64_t> lens((size_t)n);
+    for (int i = 0; i < n; i++) lens[(size_t)i] = stream_off[i + 1] - stream_off[i];
+    return decode_device_impl(c, n, d_streams, stream_off, lens.data(), d_pixels, pix_off, status);
+}
+
+int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *images, const int *heights, const int *widths, int near,
+                            int effort, uint8_t *const *outs, const size_t *out_caps, size_t *out_lens, uint8_t *const *recon, int *status) {
+    if (!c) return -1;
+    if (n < 0 || (n > 0 && (!images || !heights || !widths || !outs || !out_caps || !out_lens))) { fail(c, "bad arguments"); return -1; }
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return 0;
+    int near_c, effort_c;
+    resolve_mode(near, effort, near_c, effort_c);
+    std::vector<uint64_t> pix_off((size_t)n), stream_off((size_t)n + 1);
+    std::vector<int> st((size_t)n);
+    size_t total = 0, stream_total = 0;
+    bool want_recon = false;
+    for (int i = 0; i < n; i++) {
+        pix_off[(size_t)i] = total;
+        const bool ok = heights[i] > 0 && widths[i] > 0 && heights[i] <= 65535 && widths[i] <= 65535 && (long long)heights[i] * widths[i] <= 100000000LL;
+        if (ok) { total += align_up((size_t)heights[i] * widths[i], 256); stream_total += nblic_b200_stream_bound(heights[i], widths[i]); }
+        if (recon && recon[i]) want_recon = true;
+    }
+    want_recon = want_recon && near_c > 0;
+    CK(c->pixels.reserve(std::max<size_t>(total, 16) * (want_recon ? 2 : 1)));
+    CK(c->streams.reserve(std::max<size_t>(stream_total, 16)));
+    uint8_t *d_pix = (uint8_t *)c->pixels.p, *d_rec = want_recon ? d_pix + std::max<size_t>(total, 16) : nullptr;
+    for (int i = 0; i < n; i++) {
+        const bool ok = heights[i] > 0 && widths[i] > 0 && heights[i] <= 65535 && widths[i] <= 65535 && (long long)heights[i] * widths[i] <= 100000000LL;
+        if (ok) CK(cudaMemcpyAsync(d_pix + pix_off[(size_t)i], images[i], (size_t)heights[i] * widths[i], cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = nblic_b200_encode_batch_device(c, n, d_pix, pix_off.data(), heights, widths, near, effort, (uint8_t *)c->streams.p, c->streams.cap,
+                                            stream_off.data(), d_rec, st.data());
+    if (rc < 0) return -1;
+    int failed = 0;
+    for (int i = 0; i < n; i++) {
+        out_lens[i] = 0;
+        if (st[(size_t)i] == NBLIC_B200_OK) {
+            const size_t len = (size_t)(stream_off[(size_t)i + 1] - stream_off[(size_t)i]);
+            if (len > out_caps[i]) st[(size_t)i] = NBLIC_B200_OVERFLOW;
+            else {
+                CK(cudaMemcpyAsync(outs[i], (uint8_t *)c->streams.p + stream_off[(size_t)i], len, cudaMemcpyDeviceToHost, c->stream));
+                out_lens[i] = len;
+                if (want_recon && recon[i])
+                    CK(cudaMemcpyAsync(recon[i], d_rec + pix_off[(size_t)i], (size_t)heights[i] * widths[i], cudaMemcpyDeviceToHost, c->stream));
+            }
+        }
+        if (status) status[i] = st[(size_t)i];
+        failed += st[(size_t)i] != NBLIC_B200_OK;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return failed;
+}
+
+int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *streams, const size_t *stream_lens, uint8_t *const *images,
+                            const size_t *img_caps, int *heights, int *widths, int *nears, int *efforts, int *status) {
+    if (!c) return -1;
+    if (n < 0 || (n > 0 && (!streams || !stream_lens || !images || !img_caps))) { fail(c, "bad arguments"); return -1; }
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return 0;
+    std::vector<uint64_t> pix_off((size_t)n), stream_off((size_t)n + 1);
+    std::vector<int> st((size_t)n, NBLIC_B200_OK);
+    std::vector<Peek> peeks((size_t)n);
+    std::vector<uint64_t> lens((size_t)n);
+    size_t pix_total = 0, stream_total = 0;
+    for (int i = 0; i < n; i++) {
+        Peek p = streams[i] ? peek_bytes(streams[i], stream_lens[i]) : Peek{0, 0, 0, 0, 0, 0};
+        if (p.ok && (size_t)p.h * p.w > img_caps[i]) { p.ok = 0; st[(size_t)i] = NBLIC_B200_OVERFLOW; }
+        else if (!p.ok) st[(size_t)i] = NBLIC_B200_BAD_HEADER;
+        peeks[(size_t)i] = p;
+        if (heights) heights[i] = p.h;
+        if (widths) widths[i] = p.w;
+        if (nears) nears[i] = p.near;
+        if (efforts) efforts[i] = p.effort;
+        pix_off[(size_t)i] = pix_total;
+        stream_off[(size_t)i] = stream_total;
+        /* a stream that fails the header check still occupies a 16-byte stub so the device sees the same verdict */
+        lens[(size_t)i] = p.ok ? (uint64_t)stream_lens[i] : (uint64_t)std::min<size_t>(streams[i] ? stream_lens[i] : 0, 16);
+        if (p.ok) pix_total += align_up((size_t)p.h * p.w, 256);
+        stream_total += align_up(lens[(size_t)i], 16);
+    }
+    stream_off[(size_t)n] = stream_total;
+    CK(c->pixels.reserve(std::max<size_t>(pix_total, 16)));
+    CK(c->streams.reserve(std::max<size_t>(stream_total, 16)));
+    for (int i = 0; i < n; i++)
+        if (lens[(size_t)i]) CK(cudaMemcpyAsync((uint8_t *)c->streams.p + stream_off[(size_t)i], streams[i], lens[(size_t)i], cudaMemcpyHostToDevice, c->stream));
+    int rc = decode_device_impl(c, n, (const uint8_t *)c->streams.p, stream_off.data(), lens.data(), (uint8_t *)c->pixels.p, pix_off.data(), nullptr);
+    if (rc < 0) return -1;
+    int failed = 0;
+    for (int i = 0; i < n; i++) {
+        if (st[(size_t)i] == NBLIC_B200_OK)
+            CK(cudaMemcpyAsync(images[i], (uint8_t *)c->pixels.p + pix_off[(size_t)i], (size_t)peeks[(size_t)i].h * peeks[(size_t)i].w, cudaMemcpyDeviceToHost, c->stream));
+        if (status) status[i] = st[(size_t)i];
+        failed += st[(size_t)i] != NBLIC_B200_OK;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return failed;
+}
+
+int nblic_b200_synth_gray(nblic_b200_ctx *c, uint8_t *d_out, int height, int width, uint32_t seed, const int32_t *occluders) {
+    if (!c) return -1;
+    if (!d_out || !occluders || height <= 0 || width <= 0) { fail(c, "bad arguments"); return -1; }
+    CK(cudaSetDevice(c->device));
+    Occluders occ;
+    for (int k = 0; k < 12; k++) for (int f = 0; f < 5; f++) occ.v[k][f] = occluders[k * 5 + f];
+    const long long n = (long long)height * width;
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)c->sm_count * 16);
+    synth_gray_kernel<<<grid, 256, 0, c->stream>>>(d_out, height, width, seed, occ);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+} /* extern "C" */
