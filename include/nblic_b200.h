@@ -142,6 +142,9 @@ int nblic_b200_synth_gray(nblic_b200_ctx *ctx, uint8_t *d_out, int height, int w
  * duration (ms, on ctx's stream) of the coder kernel of the most recent batch call. */
 uint64_t nblic_b200_launch_count(const nblic_b200_ctx *ctx);
 float nblic_b200_last_coder_ms(const nblic_b200_ctx *ctx);
+/* The CUDA stream (cudaStream_t) every call of this context issues its work on, for callers that
+ * want to bracket calls with their own CUDA events. */
+void *nblic_b200_stream_handle(const nblic_b200_ctx *ctx);
 /* Name of the mapping the most recent batch call actually used ("warp" / "lane"). */
 const char *nblic_b200_last_mapping(const nblic_b200_ctx *ctx);
 /* Library version string. */

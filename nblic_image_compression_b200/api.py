@@ -31,7 +31,7 @@ SYMBOLS = [
     "nblic_b200_create", "nblic_b200_destroy", "nblic_b200_last_error", "nblic_b200_set_mapping",
     "nblic_b200_encode_batch", "nblic_b200_decode_batch", "nblic_b200_peek",
     "nblic_b200_encode_batch_device", "nblic_b200_decode_batch_device", "nblic_b200_synth_gray",
-    "nblic_b200_launch_count", "nblic_b200_last_coder_ms", "nblic_b200_last_mapping", "nblic_b200_version",
+    "nblic_b200_launch_count", "nblic_b200_last_coder_ms", "nblic_b200_last_mapping", "nblic_b200_stream_handle", "nblic_b200_version",
 ]
 
 _lib = None
@@ -68,6 +68,8 @@ def load_library() -> C.CDLL:
     lib.nblic_b200_last_coder_ms.argtypes = [C.c_void_p]
     lib.nblic_b200_last_mapping.restype = C.c_char_p
     lib.nblic_b200_last_mapping.argtypes = [C.c_void_p]
+    lib.nblic_b200_stream_handle.restype = C.c_void_p
+    lib.nblic_b200_stream_handle.argtypes = [C.c_void_p]
     lib.nblic_b200_version.restype = C.c_char_p
     lib.NBLICcompress.argtypes = [C.c_int, _u8p, _u8p, C.c_int, C.c_int, _ip, _ip]
     lib.NBLICdecompress.argtypes = [C.c_int, _u8p, _u8p, _ip, _ip, _ip, _ip]
@@ -131,6 +133,10 @@ class Codec:
     @property
     def last_coder_ms(self) -> float:
         return float(self.lib.nblic_b200_last_coder_ms(self.ctx))
+
+    @property
+    def stream_handle(self) -> int:
+        return int(self.lib.nblic_b200_stream_handle(self.ctx) or 0)
 
     @property
     def last_mapping(self) -> str:

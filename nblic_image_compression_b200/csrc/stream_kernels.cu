@@ -463,6 +463,7 @@ int nblic_b200_set_mapping(nblic_b200_ctx *c, int mapping) {
 uint64_t nblic_b200_launch_count(const nblic_b200_ctx *c) { return c ? c->launches : 0; }
 float nblic_b200_last_coder_ms(const nblic_b200_ctx *c) { return c ? c->coder_ms : 0.f; }
 const char *nblic_b200_last_mapping(const nblic_b200_ctx *c) { return c ? c->last_map : "none"; }
+void *nblic_b200_stream_handle(const nblic_b200_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 int nblic_b200_peek(const uint8_t *stream, size_t len, int *height, int *width, int *near, int *effort) {
     if (!stream) return -1;

@@ -1,0 +1,200 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the CUDA path, called through the C ABI,
+against the oracle on the same inputs, against the committed golden vectors of the unmodified
+reference, and -- at full sizes -- through round-trip properties.  Bit-exact everywhere."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import SETTINGS_EDGE, edge_cases
+from conftest import GOLDEN, sha
+from nblic_image_compression_b200.synth import gen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from nblic_image_compression_b200.build import build_library
+    build_library()
+    from nblic_image_compression_b200 import api as _api
+    return _api
+
+
+@pytest.fixture(scope="module")
+def codec(api):
+    c = api.Codec(0)  # raises when the CUDA extension or the GPU is missing: no fallback
+    yield c
+    c.close()
+
+
+def _oracle_enc(oracle, img, effort, near):
+    if effort == 0:
+        return oracle.q_encode(img), img
+    s, rec, _, _ = oracle.n_encode(img, near, effort)
+    return s, rec
+
+
+def _check_batch(api, codec, oracle, images, effort, near, mapping):
+    codec.set_mapping(mapping)
+    streams, recs, status = codec.encode_batch(images, near, effort, want_recon=near > 0)
+    assert all(s == api.OK for s in status)
+    exp = [_oracle_enc(oracle, im, effort, near) for im in images]
+    for k, (s, e) in enumerate(zip(streams, exp)):
+        assert s == e[0], f"encode e{effort} n{near} image {k} {images[k].shape}"
+        if near:
+            assert np.array_equal(recs[k], e[1]), f"reconstruction e{effort} n{near} image {k}"
+    dec = codec.decode_batch([e[0] for e in exp])
+    for k, (d, e) in enumerate(zip(dec, exp)):
+        assert d is not None and np.array_equal(d[0], e[1]), f"decode e{effort} n{near} image {k}"
+        assert (d[1], d[2]) == (near if effort else 0, effort)
+    return streams
+
+
+@pytest.mark.parametrize("effort,near", SETTINGS_EDGE)
+def test_edge_cases_vs_oracle_and_golden(api, codec, oracle, manifest, effort, near):
+    names, images = zip(*edge_cases())
+    for mapping in (api.MAP_WARP, api.MAP_LANE):
+        streams = _check_batch(api, codec, oracle, list(images), effort, near, mapping)
+        for name, s in zip(names, streams):
+            g = manifest["edge"][name]["streams"][f"e{effort}n{near}"]
+            assert len(s) == g["bytes"] and sha(s) == g["sha256"], (name, effort, near)
+
+
+def test_kodak_e0_e1_golden(api, codec, kodak, manifest):
+    """configs[0] and configs[1]: all 24 Kodak images, -e0 and -e1 lossless, bytes == reference."""
+    names = sorted(kodak)
+    images = [kodak[n] for n in names]
+    codec.set_mapping(api.MAP_WARP)
+    for key, effort in (("e0n0", 0), ("e1n0", 1)):
+        streams, _, status = codec.encode_batch(images, 0, effort)
+        assert all(s == api.OK for s in status)
+        total = 0
+        for n, s in zip(names, streams):
+            ent = manifest["kodak"][n]["streams"][key]
+            assert len(s) == ent["bytes"] and sha(s) == ent["sha256"], (n, key)
+            total += len(s)
+        assert total == {"e0n0": 4985986, "e1n0": 4891174}[key]
+        for n, d in zip(names, codec.decode_batch(streams)):
+            assert d is not None and np.array_equal(d[0], kodak[n]), (n, key)
+    # the committed reference streams decode to the Kodak pixels
+    files = [open(os.path.join(GOLDEN, "kodak_e1n0", n + ".nblic"), "rb").read() for n in names]
+    files.append(open(os.path.join(GOLDEN, "kodak_01_e0n0.nblic"), "rb").read())
+    out = codec.decode_batch(files)  # one mixed NBLIC + QNBLIC batch
+    for n, d in zip(names + ["01"], out):
+        assert d is not None and sha(d[0].tobytes()) == manifest["kodak"][n]["pixels_sha256"], n
+
+
+@pytest.mark.parametrize("key", ["e1n1", "e1n2", "e1n3"])
+def test_kodak_near_lossless_e1_golden(api, codec, kodak, manifest, key):
+    near = int(key[3])
+    names = sorted(kodak)
+    codec.set_mapping(api.MAP_WARP)
+    streams, recs, _ = codec.encode_batch([kodak[n] for n in names], near, 1, want_recon=True)
+    for n, s, r in zip(names, streams, recs):
+        ent = manifest["kodak"][n]["streams"][key]
+        assert len(s) == ent["bytes"] and sha(s) == ent["sha256"], (n, key)
+        assert sha(r.tobytes()) == ent["recon_sha256"]
+        assert int(np.abs(r.astype(int) - kodak[n].astype(int)).max()) <= near
+    for n, d, r in zip(names, codec.decode_batch(streams), recs):
+        assert np.array_equal(d[0], r)
+
+
+@pytest.mark.parametrize("effort,near", [(2, 0), (2, 2), (3, 0), (3, 1)])
+def test_avp_on_kodak_crops_and_synth(api, codec, oracle, kodak, effort, near):
+    """-e2 / -e3 (int64 least-squares predictor) on crops: the oracle needs seconds per Kodak-size image."""
+    images = [kodak[n][100:164, 200:296].copy() for n in ("01", "05", "23")] + [gen(64, 64, 0), gen(40, 333, 7)]
+    _check_batch(api, codec, oracle, images, effort, near, api.MAP_WARP)
+
+
+def test_synthetic_golden_streams(api, codec, manifest):
+    for key in ("64x64_s0", "200x333_s7", "1024x1024_s0"):
+        h, w, s = int(key.split("x")[0]), int(key.split("x")[1].split("_")[0]), int(key.split("_s")[1])
+        img = gen(h, w, s)
+        for skey, ent in manifest["synthetic"][key]["streams"].items():
+            effort, near = int(skey[1]), int(skey[3])
+            if effort >= 2 and h * w > 100_000:
+                continue  # full-size AVP streams are covered by the round-trip property test
+            streams, _, _ = codec.encode_batch([img], near, effort)
+            assert len(streams[0]) == ent["bytes"] and sha(streams[0]) == ent["sha256"], (key, skey)
+
+
+def test_device_generator_matches_numpy(api, codec):
+    import torch
+    for h, w, seed in [(64, 64, 0), (200, 333, 7), (1024, 1024, 0), (37, 1029, 123456)]:
+        d = torch.empty(h * w, dtype=torch.uint8, device="cuda:0")
+        codec.synth_device(d.data_ptr(), h, w, seed)
+        assert np.array_equal(d.cpu().numpy().reshape(h, w), gen(h, w, seed)), (h, w, seed)
+    d = torch.empty(1024 * 1024, dtype=torch.uint8, device="cuda:0")
+    codec.synth_device(d.data_ptr(), 1024, 1024, 0)
+    assert sha(d.cpu().numpy().tobytes())[:16] == "a04f5e66bcd9927f"
+
+
+def test_legacy_entry_points(api, oracle, kodak):
+    """The five reference symbols, called as src/NBLIC_main.c calls them."""
+    img = kodak["01"][:96, :160].copy()
+    q = api.legacy.qnblic_compress(img)
+    assert q == oracle.q_encode(img) and api.legacy.qnblic_compress(img, multithread=True) == q
+    assert np.array_equal(api.legacy.qnblic_decompress(q), img)
+    for near, effort in [(0, 1), (3, 1), (2, 2)]:
+        s, after, n_used, e_used = api.legacy.nblic_compress(img, near, effort)
+        exp, rec, _, _ = oracle.n_encode(img, near, effort)
+        assert s == exp and (n_used, e_used) == (near, effort)
+        assert np.array_equal(after, rec)  # near > 0 overwrites the caller's image (NBLIC.c:876,916)
+        d = api.legacy.nblic_decompress(s)
+        assert np.array_equal(d[0], rec) and d[1:] == (near, effort)
+    s, _, n_used, e_used = api.legacy.nblic_compress(img, 50, 9)  # clipped in place (NBLIC.c:768-770)
+    assert (n_used, e_used) == (9, 3) and s[13] == 9 and s[14] == 16 and s[15] == 3
+    assert api.legacy.qnblic_decompress(s) is None  # format sniff (NBLIC_main.c:223)
+    assert api.legacy.nblic_compress(np.zeros((0, 5), np.uint8), 0, 1)[0] is None
+
+
+def test_bad_and_ragged_inputs(api, codec):
+    good = codec.encode_batch([gen(8, 8, 1)], 0, 1)[0][0]
+    hdr = bytearray(good); hdr[15] = 4
+    out = codec.decode_batch([good, b"", b"NBLIC0.2" + bytes(32), bytes(hdr), good[:20]])
+    assert out[0] is not None and out[1] is None and out[2] is None and out[3] is None
+    assert out[4] is not None  # a truncated stream still decodes to *something*: the reference reads zeros past the end
+    streams, _, status = codec.encode_batch([gen(5, 7, 1), np.zeros((0, 3), np.uint8), gen(3, 3, 2)], 0, 0)
+    assert status == [api.OK, api.BAD_DIMS, api.OK] and streams[1] is None
+    small = [np.empty(16, np.uint8)]
+    _, _, status = codec.encode_batch([gen(64, 64, 5)], 0, 1, outs=small)
+    assert status == [api.OVERFLOW]
+
+
+def test_full_size_round_trip_properties(api, codec):
+    """BASELINE.json sizes the oracle cannot finish quickly: encode -> decode identity, near bound."""
+    import torch
+    codec.set_mapping(api.MAP_WARP)
+    imgs = []
+    for h, w, seed in [(1024, 1024, 11), (2048, 2048, 0), (4096, 4096, 0)]:
+        d = torch.empty(h * w, dtype=torch.uint8, device="cuda:0")
+        codec.synth_device(d.data_ptr(), h, w, seed)
+        imgs.append(d.cpu().numpy().reshape(h, w))
+    assert sha(imgs[2].tobytes())[:16] == "4a93b883b324cf8b" and sha(imgs[1].tobytes())[:16] == "4df983b5ed345fdd"
+    for effort, near in [(0, 0), (1, 0), (1, 2)]:
+        streams, recs, status = codec.encode_batch(imgs, near, effort, want_recon=near > 0)
+        assert all(s == api.OK for s in status)
+        for im, d, r in zip(imgs, codec.decode_batch(streams), recs):
+            target = r if near else im
+            assert np.array_equal(d[0], target)
+            assert int(np.abs(d[0].astype(int) - im.astype(int)).max()) <= near
+    # reference sizes / hashes of the 2048^2 and 4096^2 streams
+    s0 = codec.encode_batch(imgs[1:], 0, 0)[0]
+    assert (len(s0[0]), sha(s0[0])[:16]) == (1807312, "3fe3905a25b0e55e")
+    assert (len(s0[1]), sha(s0[1])[:16]) == (7363836, "d7dd3cd8c2e6135a")
+    s1 = codec.encode_batch(imgs[1:], 0, 1)[0]
+    assert (len(s1[0]), sha(s1[0])[:16]) == (1807398, "3e7ad084c773fd92")
+    assert (len(s1[1]), sha(s1[1])[:16]) == (7363526, "5a502f759a96971e")
+
+
+def test_lane_mapping_large_batch_matches_warp(api, codec):
+    imgs = [gen(48, 80, s) for s in range(96)]
+    codec.set_mapping(api.MAP_WARP)
+    a = codec.encode_batch(imgs, 0, 1)[0]
+    codec.set_mapping(api.MAP_LANE)
+    b = codec.encode_batch(imgs, 0, 1)[0]
+    assert a == b and codec.last_mapping == "lane"
+    for im, d in zip(imgs, codec.decode_batch(b)):
+        assert np.array_equal(d[0], im)
+    codec.set_mapping(api.MAP_AUTO)

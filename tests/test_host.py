@@ -1,0 +1,113 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports what include/nblic_b200.h
+declares, header parsing, the no-GPU failure mode (no fallback), and the multi-GPU shard planner
+under a world_size-2 gloo group."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from nblic_image_compression_b200.build import build_library
+    build_library()
+    from nblic_image_compression_b200 import api
+    return api.load_library()
+
+
+def test_header_symbols_exported(lib):
+    from nblic_image_compression_b200 import api
+    text = open(os.path.join(ROOT, "include", "nblic_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(nblic_b200_\w+|Q?NBLIC(?:de)?compress\w*)\s*\(", text))
+    assert declared, "no declarations parsed"
+    assert declared == set(api.SYMBOLS), declared ^ set(api.SYMBOLS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+
+
+def test_peek_and_bound(lib):
+    from nblic_image_compression_b200 import api
+    from conftest import GOLDEN
+    q = open(os.path.join(GOLDEN, "kodak_01_e0n0.nblic"), "rb").read()
+    n = open(os.path.join(GOLDEN, "kodak_e1n0", "04.nblic"), "rb").read()
+    assert api.peek(q[:16]) == (512, 768, 0, 0)
+    assert api.peek(n[:16]) == (768, 512, 0, 1)
+    assert api.peek(b"NBLIC0.2" + bytes(8)) is None
+    assert api.peek(b"Q0.2" + bytes(4)) is None  # zero dims (QNBLIC.c:33-45)
+    bad = bytearray(n[:16]); bad[14] = 2
+    assert api.peek(bytes(bad)) is None  # k_step below 3 (NBLIC.c:740)
+    assert api.stream_bound(512, 768) >= 2 * 512 * 768
+
+
+def test_no_gpu_means_failure_not_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from nblic_image_compression_b200 import api
+    with pytest.raises(RuntimeError):
+        api.Codec(0)
+    img = np.zeros((4, 4), np.uint8)
+    assert api.legacy.qnblic_compress(img) is None
+    s, _, near, effort = api.legacy.nblic_compress(img, 50, 0)
+    assert s is None and (near, effort) == (9, 1)  # clipped in place even when the call fails (NBLIC.c:768-770)
+
+
+def test_sniff_rejects_foreign_streams_without_cuda(lib):
+    from nblic_image_compression_b200 import api
+    from conftest import GOLDEN
+    n = open(os.path.join(GOLDEN, "kodak_e1n0", "01.nblic"), "rb").read()
+    assert api.legacy.qnblic_decompress(n) is None  # NBLIC_main.c:223 tries QNBLIC first on every file
+    assert api.legacy.nblic_decompress(b"Q0.2" + bytes(64)) is None
+
+
+def test_plan_shards_properties():
+    from nblic_image_compression_b200.shard import plan_shards
+    rng = np.random.default_rng(0)
+    px = rng.integers(1, 5_000_000, size=101).tolist()
+    for world in (1, 2, 4, 8):
+        shards = plan_shards(px, world)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(len(px)))
+        loads = [sum(px[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(px)
+    assert plan_shards([], 4) == [[], [], [], []]
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from nblic_image_compression_b200.shard import gather_streams, plan_shards
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    px = [(i * 7919) % 1000 + 1 for i in range(37)]
+    mine = plan_shards(px, world)[rank]
+    streams = [f"stream-{i}-{px[i]}".encode() for i in mine]  # stands in for the per-image .nblic bytes
+    full = gather_streams(streams, mine, len(px), dist)
+    q.put((rank, mine, full == [f"stream-{i}-{px[i]}".encode() for i in range(len(px))]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, _, ok in res)
+    assert sorted(res[0][1] + res[1][1]) == list(range(37)) and not set(res[0][1]) & set(res[1][1])
