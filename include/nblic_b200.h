@@ -88,7 +88,9 @@ enum {
     NBLIC_B200_OK = 0,
     NBLIC_B200_BAD_DIMS = 1,      /* src/NBLIC.c:717-729 / src/QNBLIC.c:33-45                       */
     NBLIC_B200_BAD_HEADER = 2,    /* src/NBLIC.c:698-712,733-745 / src/QNBLIC.c:475-486             */
-    NBLIC_B200_OVERFLOW = 3       /* output capacity too small                                      */
+    NBLIC_B200_OVERFLOW = 3,      /* output capacity too small                                      */
+    NBLIC_B200_CORRUPT = 4        /* decode only: the stream drives the coder into a state no encoder output reaches
+                                     (the reference indexes out of bounds / never returns there)    */
 };
 
 /*

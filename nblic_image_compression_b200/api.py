@@ -21,7 +21,7 @@ _u64p = C.POINTER(C.c_uint64)
 _pp = C.POINTER(C.c_void_p)
 
 MAP_AUTO, MAP_WARP, MAP_LANE = 0, 1, 2
-OK, BAD_DIMS, BAD_HEADER, OVERFLOW = 0, 1, 2, 3
+OK, BAD_DIMS, BAD_HEADER, OVERFLOW, CORRUPT = 0, 1, 2, 3, 4
 
 SYMBOLS = [
     # drop-in layer

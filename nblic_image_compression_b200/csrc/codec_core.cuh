@@ -262,6 +262,8 @@ NB_DEV int mixed_bit(RangeCoder<DEC> &rc, u32 *nu, u32 *nv, int wv, int bit) {
 }
 
 /* adaptive-Golomb binarisation over the 16x256 node forest.  R: NBLIC.c:640-679 */
+/* Returns the symbol, or -1 when a (corrupt) stream escapes past the last Golomb order -- a state no
+ * encoder output reaches (the reference indexes out of bounds there); valid streams are unaffected. */
 template <bool DEC>
 NB_DEV int golomb_symbol(RangeCoder<DEC> &rc, int k_step, u32 *forest, int u, int v, int wv, int z) {
     const int top = (N_CLASSES - 1) / k_step;
@@ -273,12 +275,16 @@ NB_DEV int golomb_symbol(RangeCoder<DEC> &rc, int k_step, u32 *forest, int u, in
         bit = mixed_bit<DEC>(rc, forest + u * 256 + node, forest + v * 256 + node, wv, bit);
         if (!bit) break;
         node += 1 << top;
-        if (node >= 256) { node >>= 1; u = v = (k + 1) * k_step; } /* escape to the next order */
+        if (node >= 256) { /* escape to the next order */
+            node >>= 1; u = v = (k + 1) * k_step;
+            if (u >= N_CLASSES) return -1;
+        }
     }
     if (DEC) z = (node >> top) << k;
     for (node++, k--; k >= 0; k--) {
         if (!DEC) bit = (z >> k) & 1;
-        bit = mixed_bit<DEC>(rc, forest + u * 256 + node, forest + v * 256 + node, wv, bit);
+        const int at = DEC ? (node & 255) : node;
+        bit = mixed_bit<DEC>(rc, forest + u * 256 + at, forest + v * 256 + at, wv, bit);
         if (DEC && bit) z += 1 << k;
         node += bit ? (1 << k) : 1;
     }
@@ -385,8 +391,8 @@ struct NJob {
     int h, w, near, k_step;
 };
 
-/* One NBLIC stream, start to finish.  Returns encode: bytes written (or ~0u on overflow); decode: 0.
- * R: NBLIC.c:749-908 */
+/* One NBLIC stream, start to finish.  Returns encode: bytes written (or ~0u on overflow); decode: 0,
+ * or 1 for a corrupt stream.  R: NBLIC.c:749-908 */
 template <int NAVP, bool DEC>
 __device__ u32 nblic_stream(const NJob &job, const NState &st) {
     constexpr int N = NAVP, M = 1 + N + N * N;
@@ -453,6 +459,7 @@ __device__ u32 nblic_stream(const NJob &job, const NState &st) {
                 z = y < N_RANKS ? (int)st.rank_of[key + y] : y;
             }
             z = golomb_symbol<DEC>(rc, k_step, st.forest, u, v, wv, z);
+            if (z < 0) return DEC ? 1u : 0xffffffffu;
             if (DEC) y = z < N_RANKS ? (int)st.sym_at[key + z] : z;
             ranker_touch(st.rank_of + key, st.sym_at + key, st.count + key, y);
 

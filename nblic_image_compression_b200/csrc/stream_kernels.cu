@@ -27,6 +27,7 @@
 
 #include "../../include/nblic_b200.h"
 #include "codec_core.cuh"
+#include "coop_nblic.cuh"
 
 using namespace nblic;
 
@@ -86,7 +87,7 @@ __device__ void run_nblic(Task &t, const NState &st, int lane, int nl) {
             if (len == 0xffffffffu) { t.status = NBLIC_B200_OVERFLOW; t.head_len = 0; }
             else t.head_len = len;
             t.tail_len = 0;
-        }
+        } else if (len != 0) t.status = NBLIC_B200_CORRUPT;
     }
     if (nl > 1) __syncwarp();
 }
@@ -143,6 +144,28 @@ __global__ void __launch_bounds__(32) coder_kernel(Task *tasks, const int *order
             st.tab = reinterpret_cast<u32 *>(base + Q_CTX_ENTRIES * 4);
             run_qnblic<DEC>(t, st, MAP == MAP_WARP ? lane : 0, MAP == MAP_WARP ? 32 : 1);
         }
+    }
+}
+
+/* Warp-cooperative lossless effort-1 encoder (coop_nblic.cuh): one warp per CTA, state in shared memory,
+ * rank-mapper frequencies in `counts` (one [512][20] int table per CTA). */
+__global__ void __launch_bounds__(32) coop_e1_encode_kernel(Task *tasks, const int *order, int n_order, int *queue, int *counts) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    CoopSmem &sm = *reinterpret_cast<CoopSmem *>(smem);
+    const int lane = threadIdx.x;
+    int *my_counts = counts + (size_t)blockIdx.x * N_RANK_ENTRIES;
+    for (;;) {
+        int pos = lane == 0 ? atomicAdd(queue, 1) : 0;
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (pos >= n_order) break;
+        Task &t = tasks[order[pos]];
+        const u32 len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, sm, my_counts, lane);
+        if (lane == 0) {
+            if (len == 0xffffffffu) { t.status = NBLIC_B200_OVERFLOW; t.head_len = 0; }
+            else t.head_len = len;
+            t.tail_len = 0;
+        }
+        __syncwarp();
     }
 }
 
@@ -278,13 +301,14 @@ struct nblic_b200_ctx {
     int device = 0;
     int sm_count = 0;
     int mapping = NBLIC_B200_MAP_AUTO;
+    bool serial_only = getenv("NBLIC_B200_SERIAL") != nullptr; /* debugging aid: force the sequential kernels */
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string error;
     uint64_t launches = 0;
     float coder_ms = 0.f;
     const char *last_map = "none";
-    DevBuf tasks, order, queue, slots, sym, cold, avp, offsets, flags, pixels, streams, recon, peeks;
+    DevBuf tasks, order, queue, slots, sym, cold, coop_counts, avp, offsets, flags, pixels, streams, recon, peeks;
     int occ_warp[2] = {0, 0};
 };
 
@@ -353,16 +377,32 @@ int launch_coder(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queu
     return launch_coder_t<KIND, DEC, MAP_LANE>(c, n_order, d_order, d_queue, plan, avp_stride);
 }
 
+int launch_coop_e1_encode(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue) {
+    const size_t smem = sizeof(CoopSmem);
+    int per_sm = 0;
+    CK(cudaFuncSetAttribute(coop_e1_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_e1_encode_kernel, 32, smem));
+    const int grid = std::min(n_order, c->sm_count * std::max(per_sm, 1));
+    CK(c->coop_counts.reserve((size_t)grid * N_RANK_ENTRIES * sizeof(int)));
+    coop_e1_encode_kernel<<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (int *)c->coop_counts.p);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 /* Upload tasks, run the coder kernels for the Q and N groups, download the task results. */
 template <bool DEC>
 int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
     const int n = (int)tasks.size();
-    std::vector<int> order_q, order_n;
+    std::vector<int> order_q, order_n, order_c; /* QNBLIC, NBLIC sequential, NBLIC warp-cooperative */
     int max_w = 1, max_effort = 0;
+    const bool coop_ok = c->mapping != NBLIC_B200_MAP_LANE && !c->serial_only;
     for (int i = 0; i < n; i++) {
         if (tasks[i].status != NBLIC_B200_OK) continue;
-        (tasks[i].effort == 0 ? order_q : order_n).push_back(i);
-        if (tasks[i].effort > 0) { max_w = std::max(max_w, tasks[i].w); max_effort = std::max(max_effort, tasks[i].effort); }
+        if (tasks[i].effort == 0) { order_q.push_back(i); continue; }
+        if (!DEC && coop_ok && tasks[i].effort == 1 && tasks[i].near == 0) { order_c.push_back(i); continue; }
+        order_n.push_back(i);
+        max_w = std::max(max_w, tasks[i].w); max_effort = std::max(max_effort, tasks[i].effort);
     }
     auto by_size = [&](int a, int b) {
         const long long pa = (long long)tasks[a].h * tasks[a].w, pb = (long long)tasks[b].h * tasks[b].w;
@@ -370,15 +410,17 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
     };
     std::sort(order_q.begin(), order_q.end(), by_size);
     std::sort(order_n.begin(), order_n.end(), by_size);
+    std::sort(order_c.begin(), order_c.end(), by_size);
 
     CK(c->tasks.reserve(sizeof(Task) * (size_t)std::max(n, 1)));
     CK(c->order.reserve(sizeof(int) * (size_t)std::max(n, 1)));
-    CK(c->queue.reserve(2 * sizeof(int)));
+    CK(c->queue.reserve(4 * sizeof(int)));
     CK(cudaMemcpyAsync(c->tasks.p, tasks.data(), sizeof(Task) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     std::vector<int> order(order_q);
     order.insert(order.end(), order_n.begin(), order_n.end());
+    order.insert(order.end(), order_c.begin(), order_c.end());
     if (!order.empty()) CK(cudaMemcpyAsync(c->order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->queue.p, 0, 2 * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->queue.p, 0, 4 * sizeof(int), c->stream));
 
     CK(cudaEventRecord(c->ev0, c->stream));
     if (!order_q.empty()) {
@@ -386,6 +428,10 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
     }
     if (!order_n.empty()) {
         if (launch_coder<KIND_N, DEC>(c, (int)order_n.size(), (const int *)c->order.p + order_q.size(), (int *)c->queue.p + 1, max_w, max_effort)) return -1;
+    }
+    if (!order_c.empty()) {
+        if (launch_coop_e1_encode(c, (int)order_c.size(), (const int *)c->order.p + order_q.size() + order_n.size(), (int *)c->queue.p + 2)) return -1;
+        c->last_map = "warp-coop";
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     return 0;
@@ -444,7 +490,7 @@ void nblic_b200_destroy(nblic_b200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->tasks, &c->order, &c->queue, &c->slots, &c->sym, &c->cold, &c->avp, &c->offsets, &c->flags, &c->pixels, &c->streams, &c->recon, &c->peeks};
+    DevBuf *bufs[] = {&c->tasks, &c->order, &c->queue, &c->slots, &c->sym, &c->cold, &c->coop_counts, &c->avp, &c->offsets, &c->flags, &c->pixels, &c->streams, &c->recon, &c->peeks};
     for (DevBuf *b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -673,10 +719,12 @@ int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *stre
     CK(c->streams.reserve(std::max<size_t>(stream_total, 16)));
     for (int i = 0; i < n; i++)
         if (lens[(size_t)i]) CK(cudaMemcpyAsync((uint8_t *)c->streams.p + stream_off[(size_t)i], streams[i], lens[(size_t)i], cudaMemcpyHostToDevice, c->stream));
-    int rc = decode_device_impl(c, n, (const uint8_t *)c->streams.p, stream_off.data(), lens.data(), (uint8_t *)c->pixels.p, pix_off.data(), nullptr);
+    std::vector<int> dev_st((size_t)n, NBLIC_B200_OK);
+    int rc = decode_device_impl(c, n, (const uint8_t *)c->streams.p, stream_off.data(), lens.data(), (uint8_t *)c->pixels.p, pix_off.data(), dev_st.data());
     if (rc < 0) return -1;
     int failed = 0;
     for (int i = 0; i < n; i++) {
+        if (st[(size_t)i] == NBLIC_B200_OK) st[(size_t)i] = dev_st[(size_t)i];
         if (st[(size_t)i] == NBLIC_B200_OK)
             CK(cudaMemcpyAsync(images[i], (uint8_t *)c->pixels.p + pix_off[(size_t)i], (size_t)peeks[(size_t)i].h * peeks[(size_t)i].w, cudaMemcpyDeviceToHost, c->stream));
         if (status) status[i] = st[(size_t)i];

@@ -154,7 +154,9 @@ def test_bad_and_ragged_inputs(api, codec):
     hdr = bytearray(good); hdr[15] = 4
     out = codec.decode_batch([good, b"", b"NBLIC0.2" + bytes(32), bytes(hdr), good[:20]])
     assert out[0] is not None and out[1] is None and out[2] is None and out[3] is None
-    assert out[4] is not None  # a truncated stream still decodes to *something*: the reference reads zeros past the end
+    # a truncated stream reads zeros past its end (like the reference) and either decodes to something
+    # or is reported corrupt; it must not fault or hang
+    assert out[4] is None or out[4][0].shape == (8, 8)
     streams, _, status = codec.encode_batch([gen(5, 7, 1), np.zeros((0, 3), np.uint8), gen(3, 3, 2)], 0, 0)
     assert status == [api.OK, api.BAD_DIMS, api.OK] and streams[1] is None
     small = [np.empty(16, np.uint8)]
