@@ -265,9 +265,9 @@ NB_DEV int mixed_bit(RangeCoder<DEC> &rc, u32 *nu, u32 *nv, int wv, int bit) {
 /* Returns the symbol, or -1 when a (corrupt) stream escapes past the last Golomb order -- a state no
  * encoder output reaches (the reference indexes out of bounds there); valid streams are unaffected. */
 template <bool DEC>
-NB_DEV int golomb_symbol(RangeCoder<DEC> &rc, int k_step, u32 *forest, int u, int v, int wv, int z) {
+NB_DEV int golomb_symbol(RangeCoder<DEC> &rc, int k_step, u32 *forest, int u, int v, int wv, int z, int node = 0) {
     const int top = (N_CLASSES - 1) / k_step;
-    int node = 0, k, bit = 0;
+    int k, bit = 0;
     if (v / k_step != u / k_step) v = u;
     for (;;) {
         k = u / k_step;

@@ -2,20 +2,26 @@
  * coop_nblic.cuh -- warp-cooperative NBLIC effort-1 coder: one coder stream per warp, the 32 lanes
  * share the work of every pixel.
  *
- *   phase P (lanes = 32 consecutive pixels)   everything that depends only on already-known pixels:
- *                                             neighbourhood sampling, the 7-direction predictor, activity,
- *                                             soft context class, texture bits            R: NBLIC.c:287-410
+ *   phase P (lanes = 32 consecutive pixels)   everything that depends only on already-known pixels.
+ *       lossless encode: the whole front end -- neighbourhood sampling, the 7-direction predictor,
+ *       activity, soft context class, texture bits                                  R: NBLIC.c:287-410
+ *       decode / near-lossless encode (reconstruction feedback): the neighbours of the two rows above
+ *       and the partial sums of every predictor cost that do not involve the pixel to the left.
  *   phase S (one pixel at a time, warp-uniform registers)
- *       bias cancel + residual fold           ctx table in shared memory                  R: NBLIC.c:413-466
- *       rank mapper                           lane s holds rank/count of symbol / rank s  R: NBLIC.c:470-523
- *       binarisation                          lane d owns decision d of the pixel: node address,
- *                                             both counter pairs, mixed probability, counter
- *                                             update -- all decisions of a pixel at once  R: NBLIC.c:589-679
- *       range coder                           consumes (bit, p) of lane 0..D-1 via __shfl R: NBLIC.c:552-586
+ *       [feedback modes] finish the predictor with a = x[j-1], e = x[j-2]            R: NBLIC.c:307-370
+ *       bias cancel + residual fold / unfold   ctx table in shared memory            R: NBLIC.c:413-466
+ *       rank mapper                            lane s holds entry s of the key's table R: NBLIC.c:470-523
+ *       binarisation, encoder                  lane d owns decision d of the pixel: node address, both
+ *                                              counter pairs, mixed probability, counter update
+ *       binarisation, decoder                  lanes evaluate every node the unary run / the suffix
+ *                                              sub-tree can reach, the coder then walks them
+ *                                                                                     R: NBLIC.c:589-679
+ *       range coder                            consumes / produces bits through __shfl; bytes move
+ *                                              through 128-byte lines held one word per lane
+ *                                                                                     R: NBLIC.c:527-586
  *
- * The lossless encoder runs phase P on the input image 32 pixels ahead; the decoder and the
- * near-lossless encoder (reconstruction feedback) use the serial kernels of codec_core.cuh.
- * Pixels whose Golomb code escapes to the next order (0.1-0.5 %) take the sequential routine.
+ * Pixels whose Golomb code escapes to the next order (0.1-0.5 %) finish in the sequential routine of
+ * codec_core.cuh on the leader lane.
  */
 #pragma once
 #include "codec_core.cuh"
@@ -24,6 +30,17 @@ namespace nblic {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+/* phase-P record of one pixel in the feedback modes (8 words, read back as two 16-byte loads) */
+struct __align__(16) PixRec {
+    u32 bcdf;   /* b | c << 8 | d << 16 | f << 24                                             */
+    u32 ghqr;   /* g | h << 8 | q << 16 | r << 24                                             */
+    u32 st_act; /* s | t << 8 | act << 16      act = |b-c| + |b-d| + |b-f| + |d-g|            */
+    u32 k01;    /* K0 | K1 << 16               Kn = the three a-free terms of directional cost n */
+    u32 k23, k45;
+    u32 k6_lin; /* K6 | (lin + 1024) << 16     lin = 9b + 2d - 2c - f                         */
+    u32 orig;   /* encoder: the original pixel                                                */
+};
+
 /* shared-memory image of one stream's adaptive state (one warp = one CTA) */
 struct CoopSmem {
     u32 forest[N_FOREST_ENTRIES];      /* 16 KB: node counters n0 | n1 << 16                          */
@@ -31,21 +48,82 @@ struct CoopSmem {
     uint8_t rank[N_RANK_ENTRIES];      /* 10 KB: encoder: symbol -> rank; decoder: rank -> symbol       */
     uint16_t soft[208];                /* activity (clamped to 200) -> u | v << 4 | wv << 8             */
 };
+/* the feedback modes add the phase-P records of the current block */
+struct CoopSmemFeedback {
+    CoopSmem st;
+    PixRec rec[32];                    /*  1 KB                                                        */
+};
 
-/* range coder whose registers are warp-uniform; only the leader lane stores bytes */
-struct CoopEncoder {
+/* ---- byte streams: a 128-byte line lives in the warp, one 32-bit word per lane ---------------- */
+
+struct LineWriter { /* base must be 128-byte aligned and private to the stream */
+    uint8_t *base;
+    u32 cap, pos, word;
+    int lane;
+    bool overflow;
+    NB_DEV void start(uint8_t *p, u32 capacity, int ln) { base = p; cap = capacity; pos = 0; word = 0; lane = ln; overflow = false; }
+    NB_DEV void flush_line(u32 line_off) {
+        const u32 at = line_off + 4u * (u32)lane;
+        if (at + 4u <= cap) *reinterpret_cast<u32 *>(base + at) = word;
+        word = 0;
+    }
+    NB_DEV void put(u32 byte) {
+        if (pos >= cap) overflow = true;
+        if ((int)((pos >> 2) & 31u) == lane) word |= (byte & 255u) << (8u * (pos & 3u));
+        pos++;
+        if ((pos & 127u) == 0) flush_line(pos - 128u);
+    }
+    NB_DEV void finish() { if (pos & 127u) flush_line(pos & ~127u); }
+};
+
+struct LineReader {
+    const uint8_t *base;
+    u32 len, pos, word;
+    unsigned long long line; /* absolute address of the cached line, 0 = none */
+    int lane;
+    NB_DEV void start(const uint8_t *p, u32 n, u32 at, int ln) { base = p; len = n; pos = at; word = 0; line = 0; lane = ln; }
+    NB_DEV u32 get() {
+        if (pos >= len) { pos++; return 0u; } /* the reference reads on; we return zeros */
+        const unsigned long long a = (unsigned long long)(base + pos);
+        if ((a & ~127ull) != line) { /* a 128-byte aligned line that holds a valid byte is always mapped */
+            line = a & ~127ull;
+            word = *reinterpret_cast<const u32 *>(line + 4ull * (unsigned)lane);
+        }
+        const u32 wsel = __shfl_sync(FULL, word, (int)((a >> 2) & 31ull));
+        pos++;
+        return (wsel >> (8u * (u32)(a & 3ull))) & 255u;
+    }
+};
+
+/* range coder with warp-uniform registers */
+template <bool DEC> struct CoopCoder;
+
+template <> struct CoopCoder<false> {
     u32 lo, hi;
-    uint8_t *wr, *wr_end;
-    bool overflow, leader;
-    NB_DEV void start(uint8_t *p, uint8_t *end, bool lead) { lo = 0; hi = 0xffffffffu; wr = p; wr_end = end; overflow = false; leader = lead; }
-    NB_DEV void put(u32 byte) { if (wr < wr_end) { if (leader) *wr = (uint8_t)byte; } else overflow = true; wr++; }
-    NB_DEV void bit(int b, u32 p1) {
+    LineWriter out;
+    NB_DEV void start() { lo = 0; hi = 0xffffffffu; }
+    NB_DEV int bit(int b, u32 p1) {
         const u32 span = hi - lo;
         const u32 mid = lo + (span >> 12) * p1 + (((span & 0xfffu) * p1) >> 12);
         if (b) hi = mid; else lo = mid + 1;
-        while (((lo ^ hi) & 0xff000000u) == 0) { put(hi >> 24); lo <<= 8; hi = (hi << 8) | 0xffu; }
+        while (((lo ^ hi) & 0xff000000u) == 0) { out.put(hi >> 24); lo <<= 8; hi = (hi << 8) | 0xffu; }
+        return b;
     }
-    NB_DEV void finish() { for (int k = 0; k < 4; k++) { put(lo >> 24); lo <<= 8; } }
+    NB_DEV void finish() { for (int k = 0; k < 4; k++) { out.put(lo >> 24); lo <<= 8; } out.finish(); }
+};
+
+template <> struct CoopCoder<true> {
+    u32 lo, hi, code;
+    LineReader in;
+    NB_DEV void start() { lo = 0; hi = 0xffffffffu; code = 0; for (int k = 0; k < 4; k++) code = (code << 8) | in.get(); }
+    NB_DEV int bit(int, u32 p1) {
+        const u32 span = hi - lo;
+        const u32 mid = lo + (span >> 12) * p1 + (((span & 0xfffu) * p1) >> 12);
+        const int b = code <= mid;
+        if (b) hi = mid; else lo = mid + 1;
+        while (((lo ^ hi) & 0xff000000u) == 0) { code = (code << 8) | in.get(); lo <<= 8; hi = (hi << 8) | 0xffu; }
+        return b;
+    }
 };
 
 NB_DEV u32 learn_packed(u32 c, int bit, int weight) { /* node_learn on the packed pair */
@@ -53,8 +131,16 @@ NB_DEV u32 learn_packed(u32 c, int bit, int weight) { /* node_learn on the packe
     if ((c & 0xffffu) + (c >> 16) > (u32)(N_MIX * 256)) c = ((c + 0x00010001u) >> 1) & 0x7fff7fffu;
     return c;
 }
+NB_DEV u32 mixed_p(u32 cu, u32 cv, int wv) { /* R: NBLIC.c:627-631 */
+    const int p = (node_p1(cu) * (N_MIX - wv) + node_p1(cv) * wv + N_MIX / 2) >> 5; /* operands >= 0: >> 5 == / 32 */
+    return (u32)clampi(p, 1, N_PROB_ONE - 1);
+}
+NB_DEV void learn_pair(u32 *forest, int u, int v, int node, u32 cu, u32 cv, int wv, int bit) {
+    if (u == v) forest[u * 256 + node] = learn_packed(learn_packed(cu, bit, N_MIX - wv), bit, wv);
+    else { forest[u * 256 + node] = learn_packed(cu, bit, N_MIX - wv); forest[v * 256 + node] = learn_packed(cv, bit, wv); }
+}
 
-/* Order tables of one stream: k = u / k_step for u = 0..15, 4 bits each. */
+/* k = u / k_step for u = 0..15, 4 bits each */
 NB_DEV unsigned long long make_order_table(int k_step) {
     unsigned long long t = 0;
     for (int u = 0; u < N_CLASSES; u++) t |= (unsigned long long)(u / k_step) << (4 * u);
@@ -62,30 +148,195 @@ NB_DEV unsigned long long make_order_table(int k_step) {
 }
 NB_DEV int order_of(unsigned long long tab, int u) { return (int)((tab >> (4 * u)) & 15u); }
 
-/*
- * Lossless effort-1 encode of one image by one warp.  `count` is the stream's rank-mapper frequency
- * table in global memory ([512][20] int, indexed by rank).  Returns the stream length in bytes or
- * 0xffffffff on overflow (identical in all lanes).
- */
-__device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, int *count, int lane) {
-    const int k_step = 3, top = (N_CLASSES - 1) / k_step; /* near = 0 (R: NBLIC.c:769) */
-    const unsigned long long ktab = make_order_table(k_step);
-
-    /* ---- reset the adaptive state ---- */
+NB_DEV void coop_reset(CoopSmem &sm, int *count, int lane) {
     for (int k = lane; k < N_FOREST_ENTRIES; k += 32) sm.forest[k] = (u32)N_MIX | ((u32)N_MIX << 16);
     for (int k = lane; k < N_CTX_ENTRIES; k += 32) sm.ctx[k] = 0;
     for (int k = lane; k < N_RANK_ENTRIES; k += 32) { const int r = k % N_RANKS; sm.rank[k] = (uint8_t)r; count[k] = 2 * (N_RANKS - 1 - r); }
     for (int d = lane; d <= 200; d += 32) { int u, v, wv; n_soft_class(d, u, v, wv); sm.soft[d] = (uint16_t)(u | (v << 4) | (wv << 8)); }
     __syncwarp();
+}
 
-    CoopEncoder rc;
-    if (lane == 0) {
-        const char magic[8] = {'N', 'B', 'L', 'I', 'C', '0', '.', '3'};
-        for (int k = 0; k < 8; k++) stream[k] = (uint8_t)magic[k];
-        stream[8] = 1; stream[9] = (uint8_t)(h >> 8); stream[10] = (uint8_t)h; stream[11] = (uint8_t)(w >> 8); stream[12] = (uint8_t)w;
-        stream[13] = 0; stream[14] = (uint8_t)k_step; stream[15] = 1;
+NB_DEV void coop_put_header(CoopCoder<false> &rc, int h, int w, int near, int k_step, int effort) { /* R: NBLIC.c:682-694 */
+    const char magic[8] = {'N', 'B', 'L', 'I', 'C', '0', '.', '3'};
+    for (int k = 0; k < 8; k++) rc.out.put((u32)magic[k]);
+    rc.out.put(1); rc.out.put((u32)h >> 8); rc.out.put((u32)h); rc.out.put((u32)w >> 8); rc.out.put((u32)w);
+    rc.out.put((u32)near); rc.out.put((u32)k_step); rc.out.put((u32)effort);
+}
+
+/* ---- encoder side of one symbol: every decision of the pixel in its own lane ------------------- */
+NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, int k_step, int top, unsigned long long ktab, int u, int v, int wv, int z,
+                               int lane) {
+    const int k = order_of(ktab, u);
+    if (order_of(ktab, v) != k) v = u;
+    const int q = z >> k;
+    const int D = q + 1 + k; /* decisions of this pixel */
+    if (q < (256 >> top) && D <= 32) {
+        int node, bit;
+        if (lane <= q) { node = lane << top; bit = lane < q; }          /* unary run, then its terminating 0 */
+        else {
+            const int t = lane - q - 1, kk = max(k - 1 - t, 0);          /* t-th suffix bit, weight 2^kk */
+            const int hi_bits = (z & ((1 << k) - 1)) & ~((2 << kk) - 1);
+            node = ((q << top) + 1 + hi_bits + t - __popc(hi_bits)) & 255;
+            bit = (z >> kk) & 1;
+        }
+        u32 coded = 0;
+        if (lane < D) {
+            const u32 cu = sm.forest[u * 256 + node], cv = sm.forest[v * 256 + node];
+            coded = mixed_p(cu, cv, wv) | ((u32)bit << 12);
+            learn_pair(sm.forest, u, v, node, cu, cv, wv, bit);
+        }
+        for (int d = 0; d < D; d++) {
+            const u32 cd = __shfl_sync(FULL, coded, d);
+            rc.bit((int)(cd >> 12), cd & 0xfffu);
+        }
+    } else { /* order escape (or an over-long unary run): sequential routine, bits replayed through the warp coder */
+        /* The leader walks the decisions in order; each (bit, p) is broadcast so every lane's coder stays in step. */
+        const int n_top = (N_CLASSES - 1) / k_step;
+        int node = 0, kk = k, uu = u, vv = v, phase = 0; /* phase 0: unary, 1: suffix, 2: done */
+        while (phase < 2) {
+            int bit;
+            if (phase == 0) bit = (node >> n_top) < (z >> kk);
+            else bit = (z >> kk) & 1;
+            const u32 cu = sm.forest[uu * 256 + node], cv = sm.forest[vv * 256 + node];
+            rc.bit(bit, mixed_p(cu, cv, wv));
+            __syncwarp();
+            if (lane == 0) learn_pair(sm.forest, uu, vv, node, cu, cv, wv, bit);
+            __syncwarp();
+            if (phase == 0) {
+                if (!bit) { node++; kk--; phase = kk >= 0 ? 1 : 2; }
+                else {
+                    node += 1 << n_top;
+                    if (node >= 256) { node >>= 1; uu = vv = (kk + 1) * k_step; kk = uu / k_step; if (uu >= N_CLASSES) { rc.out.overflow = true; phase = 2; } }
+                }
+            } else {
+                node += bit ? (1 << kk) : 1;
+                kk--;
+                if (kk < 0) phase = 2;
+            }
+        }
     }
-    rc.start(stream + 16, stream + cap, lane == 0);
+}
+
+/* ---- decoder side of one symbol ----------------------------------------------------------------- */
+/* Returns z, or -1 for a corrupt stream. */
+NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, int k_step, int top, unsigned long long ktab, int u, int v, int wv, int lane) {
+    int k = order_of(ktab, u);
+    if (order_of(ktab, v) != k) v = u;
+    const int n_unary = 256 >> top; /* unary nodes of one tree before the order escape */
+    int q = -1;
+    for (int base = 0; base < n_unary && q < 0; base += 32) {
+        /* every lane evaluates one candidate node of the unary run */
+        const int d = base + lane, node = (d << top) & 255;
+        u32 cu = 0, cv = 0, p = 0;
+        if (d < n_unary) { cu = sm.forest[u * 256 + node]; cv = sm.forest[v * 256 + node]; p = mixed_p(cu, cv, wv); }
+        const int lim = min(32, n_unary - base);
+        int stop = -1;
+        for (int dd = 0; dd < lim; dd++) {
+            const u32 pd = __shfl_sync(FULL, p, dd);
+            if (!rc.bit(0, pd)) { stop = dd; break; }
+        }
+        const int last = stop >= 0 ? stop : lim - 1;
+        if (lane <= last) learn_pair(sm.forest, u, v, node, cu, cv, wv, !(stop >= 0 && lane == stop));
+        if (stop >= 0) q = base + stop;
+    }
+    __syncwarp();
+    if (q < 0) { /* order escape: continue sequentially in the next order's tree (R: NBLIC.c:658-662) */
+        int uu = (k + 1) * k_step, node = 128;
+        for (;;) {
+            if (uu >= N_CLASSES) return -1;
+            k = uu / k_step;
+            const u32 c = sm.forest[uu * 256 + node];
+            const int bit = rc.bit(0, mixed_p(c, c, wv));
+            __syncwarp();
+            if (lane == 0) learn_pair(sm.forest, uu, uu, node, c, c, wv, bit);
+            __syncwarp();
+            if (!bit) break;
+            node += 1 << top;
+            if (node >= 256) { node >>= 1; uu = (k + 1) * k_step; }
+        }
+        int z = (node >> top) << k;
+        for (node++, k--; k >= 0; k--) {
+            const int at = node & 255;
+            const u32 c = sm.forest[uu * 256 + at];
+            const int bit = rc.bit(0, mixed_p(c, c, wv));
+            __syncwarp();
+            if (lane == 0) learn_pair(sm.forest, uu, uu, at, c, c, wv, bit);
+            __syncwarp();
+            if (bit) z += 1 << k;
+            node += bit ? (1 << k) : 1;
+        }
+        return z;
+    }
+    int z = q << k;
+    if (k > 0) { /* suffix: lane L in [1, 2^k) is the node reached by the bit prefix spelled by L below its leading 1 */
+        const int L = max(lane, 1), t = 31 - __clz(L), prefix = L ^ (1 << t);
+        const bool valid = lane >= 1 && lane < (1 << k);
+        const int node = ((q << top) + 1 + (prefix << max(k - t, 0)) + t - __popc(prefix)) & 255;
+        u32 cu = 0, cv = 0, p = 0;
+        if (valid) { cu = sm.forest[u * 256 + node]; cv = sm.forest[v * 256 + node]; p = mixed_p(cu, cv, wv); }
+        int cur = 1;
+        for (int s = 0; s < k; s++) {
+            const u32 pd = __shfl_sync(FULL, p, cur);
+            cur = 2 * cur + rc.bit(0, pd);
+        }
+        z += cur - (1 << k);
+        if (valid && (cur >> (k - t)) == lane) learn_pair(sm.forest, u, v, node, cu, cv, wv, (cur >> (k - t - 1)) & 1);
+    }
+    return z;
+}
+
+/* ---- rank mapper, lane s holds entry s of the key's table ---------------------------------------- */
+/* encoder: table = symbol -> rank.  Returns z. */
+NB_DEV int coop_rank_encode(CoopSmem &sm, int *count, int key, int y, int lane, int &my_rank, int &my_count) {
+    my_rank = lane < N_RANKS ? (int)sm.rank[key + lane] : 255;
+    my_count = lane < N_RANKS ? __ldcg(count + key + lane) : 0;
+    const int zr = __shfl_sync(FULL, my_rank, y & 31);
+    return y < N_RANKS ? zr : y;
+}
+NB_DEV void coop_rank_touch_encode(CoopSmem &sm, int *count, int key, int y, int z, int lane, int my_rank, int my_count) {
+    if (y >= N_RANKS) return;
+    const int cz = __shfl_sync(FULL, my_count, z) + 1;
+    const int cp = __shfl_sync(FULL, my_count, max(z - 1, 0));
+    const unsigned holders = __ballot_sync(FULL, my_rank == z - 1);
+    if (lane == 0) {
+        if (z > 0 && cp < cz) { /* one adjacent promotion (R: NBLIC.c:513-521) */
+            const int other = __ffs(holders) - 1;
+            count[key + z] = cp; count[key + z - 1] = cz;
+            sm.rank[key + y] = (uint8_t)(z - 1); sm.rank[key + other] = (uint8_t)z;
+        } else count[key + z] = cz;
+    }
+}
+/* decoder: table = rank -> symbol.  Returns y and performs the update. */
+NB_DEV int coop_rank_decode(CoopSmem &sm, int *count, int key, int z, int lane) {
+    if (z >= N_RANKS) return z;
+    const int my_sym = lane < N_RANKS ? (int)sm.rank[key + lane] : 255;
+    const int my_count = lane < N_RANKS ? __ldcg(count + key + lane) : 0;
+    const int y = __shfl_sync(FULL, my_sym, z);
+    const int other = __shfl_sync(FULL, my_sym, max(z - 1, 0));
+    const int cz = __shfl_sync(FULL, my_count, z) + 1;
+    const int cp = __shfl_sync(FULL, my_count, max(z - 1, 0));
+    if (lane == 0) {
+        if (z > 0 && cp < cz) {
+            count[key + z] = cp; count[key + z - 1] = cz;
+            sm.rank[key + z] = (uint8_t)other; sm.rank[key + z - 1] = (uint8_t)y;
+        } else count[key + z] = cz;
+    }
+    return y;
+}
+
+/*
+ * Lossless effort-1 encode of one image by one warp (phase P covers the whole front end).
+ * `count`: the stream's rank-mapper frequency table in global memory ([512][20] int, indexed by rank).
+ * `stream` must be 128-byte aligned.  Returns the stream length or 0xffffffff on overflow.
+ */
+__device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, int *count, int lane) {
+    const int k_step = 3, top = (N_CLASSES - 1) / k_step; /* near = 0 (R: NBLIC.c:769) */
+    const unsigned long long ktab = make_order_table(k_step);
+    coop_reset(sm, count, lane);
+    CoopCoder<false> rc;
+    rc.out.start(stream, cap, lane);
+    coop_put_header(rc, h, w, 0, k_step, 1);
+    rc.start();
 
     for (int i = 0; i < h; i++) {
         int carry_px0 = 0; /* px0 of the pixel left of this block */
@@ -111,9 +362,7 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
                 const u32 r0 = __shfl_sync(FULL, rec0, jj);
                 const int adr_s = (int)__shfl_sync(FULL, adr, jj);
                 const int s_px0 = r0 & 255, s_x = (r0 >> 8) & 255;
-                const int u = (r0 >> 16) & 15;
-                int v = (r0 >> 20) & 15;
-                const int wv = (r0 >> 24) & 31;
+                const int u = (r0 >> 16) & 15, v = (r0 >> 20) & 15, wv = (r0 >> 24) & 31;
 
                 /* bias cancel, residual fold, context update (R: NBLIC.c:413-466) */
                 const int c = sm.ctx[adr_s];
@@ -123,71 +372,164 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
                 const int y = mag == 0 ? 0 : (mag <= room ? 2 * mag - ((s_x >= px) ^ sign) : mag + room);
                 if (lane == 0) sm.ctx[adr_s] = (int16_t)n_bias_learn(c, clampi(s_x - s_px0, -127, 127));
 
-                /* rank mapper: lane s < 20 holds rank_of[s] and count[s] of this (px, sign) key */
                 const int key = ((px << 1) | sign) * N_RANKS;
-                const int my_rank = lane < N_RANKS ? (int)sm.rank[key + lane] : 255;
-                const int my_count = lane < N_RANKS ? __ldcg(count + key + lane) : 0;
-                const int z_ranked = __shfl_sync(FULL, my_rank, y & 31);
-                const int z = y < N_RANKS ? z_ranked : y;
-
-                /* binarisation (R: NBLIC.c:640-679) */
-                const int k = order_of(ktab, u);
-                if (order_of(ktab, v) != k) v = u;
-                const int q = z >> k;
-                if (q < (256 >> top)) {
-                    const int D = q + 1 + k; /* decisions of this pixel, one per lane */
-                    int node, bit;
-                    if (lane <= q) { node = lane << top; bit = lane < q; }
-                    else {
-                        const int t = lane - q - 1, kk = k - 1 - t;          /* t-th suffix bit, weight 2^kk */
-                        const int hi_bits = (z & ((1 << k) - 1)) & ~((2 << max(kk, 0)) - 1);
-                        node = (q << top) + 1 + hi_bits + t - __popc(hi_bits);
-                        bit = (z >> max(kk, 0)) & 1;
-                    }
-                    u32 coded = 0;
-                    if (lane < D) {
-                        u32 *nu = sm.forest + u * 256 + node, *nv = sm.forest + v * 256 + node;
-                        const u32 cu = *nu, cv = *nv;
-                        const int p = (node_p1(cu) * (N_MIX - wv) + node_p1(cv) * wv + N_MIX / 2) >> 5;
-                        coded = (u32)clampi(p, 1, N_PROB_ONE - 1) | ((u32)bit << 12);
-                        if (u == v) *nu = learn_packed(learn_packed(cu, bit, N_MIX - wv), bit, wv);
-                        else { *nu = learn_packed(cu, bit, N_MIX - wv); *nv = learn_packed(cv, bit, wv); }
-                    }
-                    for (int d = 0; d < D; d++) {
-                        const u32 cd = __shfl_sync(FULL, coded, d);
-                        rc.bit((int)(cd >> 12), cd & 0xfffu);
-                    }
-                } else { /* order escape: sequential routine on the leader, coder registers re-broadcast */
-                    if (lane == 0) {
-                        RangeCoder<false> seq;
-                        seq.lo = rc.lo; seq.hi = rc.hi; seq.wr = rc.wr; seq.wr_end = rc.wr_end; seq.overflow = rc.overflow;
-                        golomb_symbol<false>(seq, k_step, sm.forest, u, v, wv, z);
-                        rc.lo = seq.lo; rc.hi = seq.hi; rc.wr = seq.wr; rc.overflow = seq.overflow;
-                    }
-                    rc.lo = __shfl_sync(FULL, rc.lo, 0); rc.hi = __shfl_sync(FULL, rc.hi, 0);
-                    rc.wr = stream + __shfl_sync(FULL, (u32)(rc.wr - stream), 0);
-                    rc.overflow = __shfl_sync(FULL, (int)rc.overflow, 0) != 0;
-                }
-
-                /* rank mapper update (R: NBLIC.c:500-523) */
-                if (y < N_RANKS) {
-                    const int cz = __shfl_sync(FULL, my_count, z) + 1;
-                    const int cp = __shfl_sync(FULL, my_count, max(z - 1, 0));
-                    const unsigned holders = __ballot_sync(FULL, my_rank == z - 1);
-                    if (lane == 0) {
-                        if (z > 0 && cp < cz) { /* one adjacent promotion */
-                            const int other = __ffs(holders) - 1;
-                            count[key + z] = cp; count[key + z - 1] = cz;
-                            sm.rank[key + y] = (uint8_t)(z - 1); sm.rank[key + other] = (uint8_t)z;
-                        } else count[key + z] = cz;
-                    }
-                }
+                int my_rank, my_count;
+                const int z = coop_rank_encode(sm, count, key, y, lane, my_rank, my_count);
+                coop_encode_symbol(rc, sm, k_step, top, ktab, u, v, wv, z, lane);
+                coop_rank_touch_encode(sm, count, key, y, z, lane, my_rank, my_count);
                 __syncwarp();
             }
         }
     }
     rc.finish();
-    return rc.overflow ? 0xffffffffu : (u32)(rc.wr - stream);
+    return rc.out.overflow ? 0xffffffffu : rc.out.pos;
+}
+
+/*
+ * Effort-1 stream with reconstruction feedback: the decoder (any near) and the near-lossless encoder.
+ * `rec` receives the decoded / reconstructed raster and is the source of every neighbour.
+ * Encoder: `stream` 128-byte aligned, cap = capacity; returns length or 0xffffffff.
+ * Decoder: cap = valid bytes; returns 0, or 1 for a corrupt stream.
+ */
+template <bool DEC>
+__device__ u32 coop_e1_feedback(const uint8_t *src, uint8_t *rec, int h, int w, int near, int k_step, uint8_t *stream, u32 cap,
+                                CoopSmemFeedback &smf, int *count, int lane) {
+    CoopSmem &sm = smf.st;
+    const int top = (N_CLASSES - 1) / k_step;
+    const unsigned long long ktab = make_order_table(k_step);
+    const int qn = 2 * near + 1;
+    const u32 qmagic = 65536u / (u32)qn + 1u; /* n / qn == (n * qmagic) >> 16 for 0 <= n < 3400 */
+    coop_reset(sm, count, lane);
+    CoopCoder<DEC> rc;
+    if constexpr (DEC) { rc.in.start(stream, cap, 16, lane); }
+    else { rc.out.start(stream, cap, lane); coop_put_header(rc, h, w, near, k_step, 1); }
+    rc.start();
+
+    for (int i = 0; i < h; i++) {
+        int err = 0, x1 = 0, x2 = 0; /* previous two pixels of this row */
+        uint8_t *row = rec + (size_t)i * w;
+        for (int j0 = 0; j0 < w; j0 += 32) {
+            /* ---------------- phase P: the rows above, lane = pixel j0 + lane ---------------- */
+            {
+                const int j = min(j0 + lane, w - 1);
+                PixRec pr;
+                pr.orig = DEC ? 0u : (u32)src[(size_t)i * w + j];
+                if (i >= 1) {
+                    const uint8_t *r1 = row - w, *r2 = r1 - w;
+                    const bool up2 = i >= 2, l1 = j >= 1, l2 = j >= 2, rt1 = j + 1 < w, rt2 = j + 2 < w;
+                    const int b = r1[j];
+                    const int c = l1 ? (int)r1[j - 1] : b;
+                    const int d = rt1 ? (int)r1[j + 1] : b;
+                    const int f = up2 ? (int)r2[j] : b;
+                    const int g = (up2 && rt1) ? (int)r2[j + 1] : f;
+                    const int hh = (up2 && l1) ? (int)r2[j - 1] : f;
+                    const int q = l2 ? (int)r1[j - 2] : c;
+                    const int r = (up2 && rt2) ? (int)r2[j + 2] : g;
+                    const int s = (up2 && l2) ? (int)r2[j - 2] : hh;
+                    const int t = rt2 ? (int)r1[j + 2] : d;
+                    pr.bcdf = (u32)b | ((u32)c << 8) | ((u32)d << 16) | ((u32)f << 24);
+                    pr.ghqr = (u32)g | ((u32)hh << 8) | ((u32)q << 16) | ((u32)r << 24);
+                    const int act = abs(b - c) + abs(b - d) + abs(b - f) + abs(d - g);
+                    pr.st_act = (u32)s | ((u32)t << 8) | ((u32)act << 16);
+                    const int K0 = abs(c - q) + abs(b - c) + abs(d - b);
+                    const int K1 = abs(c - hh) + abs(b - f) + abs(d - g);
+                    const int K2 = abs(c - s) + abs(b - hh) + abs(d - f);
+                    const int K3 = abs(c - f) + abs(b - g) + abs(d - r);
+                    const int K4 = abs(2 * c - q - s) + abs(2 * b - c - hh) + abs(2 * d - b - f);
+                    const int K5 = abs(2 * c - s - hh) + abs(2 * b - hh - f) + abs(2 * d - f - g);
+                    const int K6 = abs(2 * c - hh - f) + abs(2 * b - f - g) + abs(2 * d - g - r);
+                    pr.k01 = (u32)K0 | ((u32)K1 << 16); pr.k23 = (u32)K2 | ((u32)K3 << 16); pr.k45 = (u32)K4 | ((u32)K5 << 16);
+                    pr.k6_lin = (u32)K6 | ((u32)(9 * b + 2 * d - 2 * c - f + 1024) << 16);
+                } else { pr.bcdf = pr.ghqr = pr.st_act = pr.k01 = pr.k23 = pr.k45 = pr.k6_lin = 0; }
+                smf.rec[lane] = pr;
+                __syncwarp();
+            }
+
+            /* ---------------- phase S: one pixel at a time ---------------- */
+            const int n_here = min(32, w - j0);
+            u32 my_x = 0;
+            for (int jj = 0; jj < n_here; jj++) {
+                const int j = j0 + jj;
+                const uint4 ra = *reinterpret_cast<const uint4 *>(&smf.rec[jj]);
+                const uint4 rb = *(reinterpret_cast<const uint4 *>(&smf.rec[jj]) + 1);
+                Nb nb;
+                int px0;
+                if (i >= 1) {
+                    nb.b = ra.x & 255; nb.c = (ra.x >> 8) & 255; nb.d = (ra.x >> 16) & 255; nb.f = ra.x >> 24;
+                    nb.g = ra.y & 255; nb.q = (ra.y >> 16) & 255;
+                    nb.a = j == 0 ? nb.b : x1;
+                    nb.e = j >= 2 ? x2 : nb.a;
+                    const int a = nb.a, e = nb.e;
+                    const int c0 = 2 * (abs(a - e) + (int)(ra.w & 0xffffu)), c1 = 2 * (abs(a - nb.c) + (int)(ra.w >> 16));
+                    const int c2 = 2 * (abs(a - nb.q) + (int)(rb.x & 0xffffu)), c3 = 2 * (abs(a - nb.b) + (int)(rb.x >> 16));
+                    const int c4 = abs(2 * a - e - nb.q) + (int)(rb.y & 0xffffu), c5 = abs(2 * a - nb.q - nb.c) + (int)(rb.y >> 16);
+                    const int c6 = abs(2 * a - nb.c - nb.b) + (int)(rb.z & 0xffffu);
+                    Pred pt;
+                    int best = c0;
+                    pt.ang2 = 2 * a;
+                    if (c1 < best) { best = c1; pt.ang2 = 2 * nb.b; }
+                    if (c2 < best) { best = c2; pt.ang2 = 2 * nb.c; }
+                    if (c3 < best) { best = c3; pt.ang2 = 2 * nb.d; }
+                    if (c4 < best) { best = c4; pt.ang2 = a + nb.c; }
+                    if (c5 < best) { best = c5; pt.ang2 = nb.c + nb.b; }
+                    if (c6 < best) { best = c6; pt.ang2 = nb.b + nb.d; }
+                    pt.spread = c0 + c1 + c2 + c3 + c4 + c5 + c6 - 7 * best;
+                    pt.lin16 = clampi(9 * a + (int)(rb.z >> 16) - 1024 - e, 0, 16 * 255);
+                    px0 = blend_prediction(pt, n_weight(pt.spread));
+                } else { /* first row: every neighbour falls back to the pixel on the left (R: NBLIC.c:288-303) */
+                    const int a = j >= 1 ? x1 : 128;
+                    nb.a = nb.b = nb.c = nb.d = nb.f = nb.g = nb.h = nb.q = nb.r = nb.s = nb.t = a;
+                    nb.e = j >= 2 ? x2 : a;
+                    const Pred pt = predictor_terms(nb);
+                    px0 = blend_prediction(pt, n_weight(pt.spread));
+                }
+                const int act = i >= 1 ? abs(nb.a - nb.e) + abs(nb.a - nb.c) + (int)(ra.z >> 16) + 2 * abs(err) : activity(nb, err);
+                const u32 soft = sm.soft[min(act, 200)];
+                const int u = soft & 15, v = (soft >> 4) & 15, wv = (soft >> 8) & 31;
+                const int adr = ((u >> 1) << 8) | texture_bits(nb, px0);
+                const int c = sm.ctx[adr];
+                int px, sign;
+                n_bias_apply(c, px0, px, sign);
+                const int key = ((px << 1) | sign) * N_RANKS;
+                const int room = (int)(((u32)(min(px, 255 - px) + near) * qmagic) >> 16);
+
+                int y;
+                if constexpr (DEC) {
+                    const int z = coop_decode_symbol(rc, sm, k_step, top, ktab, u, v, wv, lane);
+                    if (z < 0) return 1u;
+                    y = coop_rank_decode(sm, count, key, z, lane);
+                } else {
+                    const int xo = (int)rb.w;
+                    const int mag = (int)(((u32)(abs(xo - px) + near) * qmagic) >> 16);
+                    y = mag <= 0 ? 0 : (mag <= room ? 2 * mag - ((xo >= px) ^ sign) : mag + room);
+                    int my_rank, my_count;
+                    const int z = coop_rank_encode(sm, count, key, y, lane, my_rank, my_count);
+                    coop_encode_symbol(rc, sm, k_step, top, ktab, u, v, wv, z, lane);
+                    coop_rank_touch_encode(sm, count, key, y, z, lane, my_rank, my_count);
+                }
+
+                /* reconstruction (R: NBLIC.c:449-466) */
+                int mag, up;
+                if (y <= 0) { mag = 0; up = 0; }
+                else if (y <= 2 * room) { mag = (y + 1) >> 1; up = (y & 1) ^ sign; }
+                else { mag = y - room; up = px < 128; }
+                mag *= qn;
+                const int x = clampi(up ? px + mag : px - mag, 0, 255);
+                if (lane == jj) my_x = (u32)x;
+                err = clampi(x - px0, -127, 127);
+                if (lane == 0) sm.ctx[adr] = (int16_t)n_bias_learn(c, err);
+                x2 = x1; x1 = x;
+                __syncwarp();
+            }
+            if (lane < n_here) row[j0 + lane] = (uint8_t)my_x; /* one coalesced store per block */
+            __syncwarp();
+        }
+    }
+    if constexpr (DEC) return 0u;
+    else {
+        rc.finish();
+        return rc.out.overflow ? 0xffffffffu : rc.out.pos;
+    }
 }
 
 } /* namespace nblic */

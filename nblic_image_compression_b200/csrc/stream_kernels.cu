@@ -147,11 +147,12 @@ __global__ void __launch_bounds__(32) coder_kernel(Task *tasks, const int *order
     }
 }
 
-/* Warp-cooperative lossless effort-1 encoder (coop_nblic.cuh): one warp per CTA, state in shared memory,
- * rank-mapper frequencies in `counts` (one [512][20] int table per CTA). */
-__global__ void __launch_bounds__(32) coop_e1_encode_kernel(Task *tasks, const int *order, int n_order, int *queue, int *counts) {
+/* Warp-cooperative effort-1 kernels (coop_nblic.cuh): one warp per CTA, adaptive state in shared memory,
+ * rank-mapper frequencies in `counts` (one [512][20] int table per CTA).
+ * MODE 0: lossless encode (phase P = whole front end); 1: near-lossless encode; 2: decode. */
+template <int MODE>
+__global__ void __launch_bounds__(32) coop_e1_kernel(Task *tasks, const int *order, int n_order, int *queue, int *counts) {
     extern __shared__ __align__(16) uint8_t smem[];
-    CoopSmem &sm = *reinterpret_cast<CoopSmem *>(smem);
     const int lane = threadIdx.x;
     int *my_counts = counts + (size_t)blockIdx.x * N_RANK_ENTRIES;
     for (;;) {
@@ -159,11 +160,17 @@ __global__ void __launch_bounds__(32) coop_e1_encode_kernel(Task *tasks, const i
         pos = __shfl_sync(0xffffffffu, pos, 0);
         if (pos >= n_order) break;
         Task &t = tasks[order[pos]];
-        const u32 len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, sm, my_counts, lane);
+        u32 len;
+        if (MODE == 0) len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, *reinterpret_cast<CoopSmem *>(smem), my_counts, lane);
+        else len = coop_e1_feedback<MODE == 2>(t.src, t.rec, t.h, t.w, t.near, t.k_step, t.slot, t.slot_cap,
+                                               *reinterpret_cast<CoopSmemFeedback *>(smem), my_counts, lane);
         if (lane == 0) {
-            if (len == 0xffffffffu) { t.status = NBLIC_B200_OVERFLOW; t.head_len = 0; }
-            else t.head_len = len;
-            t.tail_len = 0;
+            if (MODE == 2) { if (len != 0) t.status = NBLIC_B200_CORRUPT; }
+            else {
+                if (len == 0xffffffffu) { t.status = NBLIC_B200_OVERFLOW; t.head_len = 0; }
+                else t.head_len = len;
+                t.tail_len = 0;
+            }
         }
         __syncwarp();
     }
@@ -377,14 +384,15 @@ int launch_coder(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queu
     return launch_coder_t<KIND, DEC, MAP_LANE>(c, n_order, d_order, d_queue, plan, avp_stride);
 }
 
-int launch_coop_e1_encode(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue) {
-    const size_t smem = sizeof(CoopSmem);
+template <int MODE>
+int launch_coop_e1(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue) {
+    const size_t smem = MODE == 0 ? sizeof(CoopSmem) : sizeof(CoopSmemFeedback);
     int per_sm = 0;
-    CK(cudaFuncSetAttribute(coop_e1_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_e1_encode_kernel, 32, smem));
+    CK(cudaFuncSetAttribute(coop_e1_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_e1_kernel<MODE>, 32, smem));
     const int grid = std::min(n_order, c->sm_count * std::max(per_sm, 1));
     CK(c->coop_counts.reserve((size_t)grid * N_RANK_ENTRIES * sizeof(int)));
-    coop_e1_encode_kernel<<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (int *)c->coop_counts.p);
+    coop_e1_kernel<MODE><<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (int *)c->coop_counts.p);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -394,13 +402,16 @@ int launch_coop_e1_encode(nblic_b200_ctx *c, int n_order, const int *d_order, in
 template <bool DEC>
 int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
     const int n = (int)tasks.size();
-    std::vector<int> order_q, order_n, order_c; /* QNBLIC, NBLIC sequential, NBLIC warp-cooperative */
+    std::vector<int> order_q, order_n, order_c, order_f; /* QNBLIC, NBLIC sequential, NBLIC warp-cooperative (lossless encode / feedback) */
     int max_w = 1, max_effort = 0;
     const bool coop_ok = c->mapping != NBLIC_B200_MAP_LANE && !c->serial_only;
     for (int i = 0; i < n; i++) {
         if (tasks[i].status != NBLIC_B200_OK) continue;
         if (tasks[i].effort == 0) { order_q.push_back(i); continue; }
-        if (!DEC && coop_ok && tasks[i].effort == 1 && tasks[i].near == 0) { order_c.push_back(i); continue; }
+        if (coop_ok && tasks[i].effort == 1) { /* warp-cooperative kernels; lossless encodes first */
+            if (!DEC && tasks[i].near == 0) order_c.push_back(i); else order_f.push_back(i);
+            continue;
+        }
         order_n.push_back(i);
         max_w = std::max(max_w, tasks[i].w); max_effort = std::max(max_effort, tasks[i].effort);
     }
@@ -411,6 +422,7 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
     std::sort(order_q.begin(), order_q.end(), by_size);
     std::sort(order_n.begin(), order_n.end(), by_size);
     std::sort(order_c.begin(), order_c.end(), by_size);
+    std::sort(order_f.begin(), order_f.end(), by_size);
 
     CK(c->tasks.reserve(sizeof(Task) * (size_t)std::max(n, 1)));
     CK(c->order.reserve(sizeof(int) * (size_t)std::max(n, 1)));
@@ -419,6 +431,7 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
     std::vector<int> order(order_q);
     order.insert(order.end(), order_n.begin(), order_n.end());
     order.insert(order.end(), order_c.begin(), order_c.end());
+    order.insert(order.end(), order_f.begin(), order_f.end());
     if (!order.empty()) CK(cudaMemcpyAsync(c->order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->queue.p, 0, 4 * sizeof(int), c->stream));
 
@@ -430,7 +443,12 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
         if (launch_coder<KIND_N, DEC>(c, (int)order_n.size(), (const int *)c->order.p + order_q.size(), (int *)c->queue.p + 1, max_w, max_effort)) return -1;
     }
     if (!order_c.empty()) {
-        if (launch_coop_e1_encode(c, (int)order_c.size(), (const int *)c->order.p + order_q.size() + order_n.size(), (int *)c->queue.p + 2)) return -1;
+        if (launch_coop_e1<0>(c, (int)order_c.size(), (const int *)c->order.p + order_q.size() + order_n.size(), (int *)c->queue.p + 2)) return -1;
+        c->last_map = "warp-coop";
+    }
+    if (!order_f.empty()) {
+        const int *d_ord = (const int *)c->order.p + order_q.size() + order_n.size() + order_c.size();
+        if (DEC ? launch_coop_e1<2>(c, (int)order_f.size(), d_ord, (int *)c->queue.p + 3) : launch_coop_e1<1>(c, (int)order_f.size(), d_ord, (int *)c->queue.p + 3)) return -1;
         c->last_map = "warp-coop";
     }
     CK(cudaEventRecord(c->ev1, c->stream));
