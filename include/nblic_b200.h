@@ -140,6 +140,10 @@ int nblic_b200_decode_batch_device(nblic_b200_ctx *ctx, int n, const uint8_t *d_
 int nblic_b200_synth_gray(nblic_b200_ctx *ctx, uint8_t *d_out, int height, int width, uint32_t seed,
                           const int32_t *occluders);
 
+/* Test hook: out[i] = trunc(num[i] / den[i]) computed by the kernels' reciprocal-based exact 64-bit
+ * division (csrc/coop_avp.cuh: div_rcp); den[i] == 0 yields 0.  Host arrays. */
+int nblic_b200_debug_divcheck(nblic_b200_ctx *ctx, const int64_t *num, const int64_t *den, int n, int64_t *out);
+
 /* Instrumentation for bench.py: kernels launched by this context so far, and the CUDA-event
  * duration (ms, on ctx's stream) of the coder kernel of the most recent batch call. */
 uint64_t nblic_b200_launch_count(const nblic_b200_ctx *ctx);

@@ -30,7 +30,7 @@ SYMBOLS = [
     # batch layer
     "nblic_b200_create", "nblic_b200_destroy", "nblic_b200_last_error", "nblic_b200_set_mapping",
     "nblic_b200_encode_batch", "nblic_b200_decode_batch", "nblic_b200_peek",
-    "nblic_b200_encode_batch_device", "nblic_b200_decode_batch_device", "nblic_b200_synth_gray",
+    "nblic_b200_encode_batch_device", "nblic_b200_decode_batch_device", "nblic_b200_synth_gray", "nblic_b200_debug_divcheck",
     "nblic_b200_launch_count", "nblic_b200_last_coder_ms", "nblic_b200_last_mapping", "nblic_b200_stream_handle", "nblic_b200_version",
 ]
 
@@ -62,6 +62,7 @@ def load_library() -> C.CDLL:
                                                    C.c_void_p, C.c_uint64, _u64p, C.c_void_p, _ip]
     lib.nblic_b200_decode_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, _u64p, C.c_void_p, _u64p, _ip]
     lib.nblic_b200_synth_gray.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int32)]
+    lib.nblic_b200_debug_divcheck.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.nblic_b200_launch_count.restype = C.c_uint64
     lib.nblic_b200_launch_count.argtypes = [C.c_void_p]
     lib.nblic_b200_last_coder_ms.restype = C.c_float
@@ -210,6 +211,14 @@ class Codec:
         if rc < 0:
             raise RuntimeError("nblic_b200_decode_batch_device: " + self._err())
         return status[:n], rc
+
+    def divcheck(self, num: np.ndarray, den: np.ndarray) -> np.ndarray:
+        num = np.ascontiguousarray(num, dtype=np.int64)
+        den = np.ascontiguousarray(den, dtype=np.int64)
+        out = np.zeros_like(num)
+        if self.lib.nblic_b200_debug_divcheck(self.ctx, num.ctypes.data, den.ctypes.data, len(num), out.ctypes.data) != 0:
+            raise RuntimeError("nblic_b200_debug_divcheck: " + self._err())
+        return out
 
     def synth_device(self, d_out: int, h: int, w: int, seed: int):
         from .synth import occluders

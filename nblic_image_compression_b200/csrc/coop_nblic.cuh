@@ -25,6 +25,7 @@
  */
 #pragma once
 #include "codec_core.cuh"
+#include "coop_avp.cuh"
 
 namespace nblic {
 
@@ -52,6 +53,11 @@ struct CoopSmem {
 struct CoopSmemFeedback {
     CoopSmem st;
     PixRec rec[32];                    /*  1 KB                                                        */
+};
+/* efforts 2 / 3 add the two augmented systems of the least-squares predictor */
+struct CoopSmemAvp {
+    CoopSmemFeedback fb;
+    AvpSmem avp;
 };
 
 /* ---- byte streams: a 128-byte line lives in the warp, one 32-bit word per lane ---------------- */
@@ -386,28 +392,38 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
 }
 
 /*
- * Effort-1 stream with reconstruction feedback: the decoder (any near) and the near-lossless encoder.
- * `rec` receives the decoded / reconstructed raster and is the source of every neighbour.
+ * Stream with a per-pixel sequential front end: the decoder (any near), the near-lossless encoder, and
+ * every effort-2/3 stream (NAVP = 6 / 10: the AVP accumulators form a pixel-to-pixel chain even when
+ * the pixels are known).  `nbimg` is the raster the neighbours come from, `out_rec` (may be NULL when
+ * nbimg is the source image) receives the decoded / reconstructed pixels.
  * Encoder: `stream` 128-byte aligned, cap = capacity; returns length or 0xffffffff.
  * Decoder: cap = valid bytes; returns 0, or 1 for a corrupt stream.
  */
-template <bool DEC>
-__device__ u32 coop_e1_feedback(const uint8_t *src, uint8_t *rec, int h, int w, int near, int k_step, uint8_t *stream, u32 cap,
-                                CoopSmemFeedback &smf, int *count, int lane) {
+template <int NAVP, bool DEC>
+__device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *out_rec, int h, int w, int near, int k_step, uint8_t *stream,
+                             u32 cap, CoopSmemFeedback &smf, AvpSmem *avp_sm, i64 *Brow, i64 *Frow, int *count, int lane) {
     CoopSmem &sm = smf.st;
+    constexpr int AN = NAVP > 0 ? NAVP : 1;
+    constexpr int AM = AvpGeom<AN>::M, ANS = AvpGeom<AN>::NS;
     const int top = (N_CLASSES - 1) / k_step;
     const unsigned long long ktab = make_order_table(k_step);
     const int qn = 2 * near + 1;
     const u32 qmagic = 65536u / (u32)qn + 1u; /* n / qn == (n * qmagic) >> 16 for 0 <= n < 3400 */
     coop_reset(sm, count, lane);
+    i64 E[ANS], ridge = 8;
+    if constexpr (NAVP > 0) {
+        for (size_t k = lane; k < (size_t)w * AM; k += 32) Brow[k] = 0;
+        __syncwarp();
+    }
     CoopCoder<DEC> rc;
     if constexpr (DEC) { rc.in.start(stream, cap, 16, lane); }
-    else { rc.out.start(stream, cap, lane); coop_put_header(rc, h, w, near, k_step, 1); }
+    else { rc.out.start(stream, cap, lane); coop_put_header(rc, h, w, near, k_step, NAVP == 0 ? 1 : (NAVP == 6 ? 2 : 3)); }
     rc.start();
 
     for (int i = 0; i < h; i++) {
         int err = 0, x1 = 0, x2 = 0; /* previous two pixels of this row */
-        uint8_t *row = rec + (size_t)i * w;
+        const uint8_t *row = nbimg + (size_t)i * w;
+        if constexpr (NAVP > 0) { avp_row_start<AN>(E, Brow, Frow, w, lane); __syncwarp(); }
         for (int j0 = 0; j0 < w; j0 += 32) {
             /* ---------------- phase P: the rows above, lane = pixel j0 + lane ---------------- */
             {
@@ -453,35 +469,56 @@ __device__ u32 coop_e1_feedback(const uint8_t *src, uint8_t *rec, int h, int w, 
                 const uint4 ra = *reinterpret_cast<const uint4 *>(&smf.rec[jj]);
                 const uint4 rb = *(reinterpret_cast<const uint4 *>(&smf.rec[jj]) + 1);
                 Nb nb;
-                int px0;
                 if (i >= 1) {
                     nb.b = ra.x & 255; nb.c = (ra.x >> 8) & 255; nb.d = (ra.x >> 16) & 255; nb.f = ra.x >> 24;
-                    nb.g = ra.y & 255; nb.q = (ra.y >> 16) & 255;
+                    nb.g = ra.y & 255; nb.h = (ra.y >> 8) & 255; nb.q = (ra.y >> 16) & 255; nb.r = ra.y >> 24;
+                    nb.s = ra.z & 255; nb.t = (ra.z >> 8) & 255;
                     nb.a = j == 0 ? nb.b : x1;
                     nb.e = j >= 2 ? x2 : nb.a;
-                    const int a = nb.a, e = nb.e;
-                    const int c0 = 2 * (abs(a - e) + (int)(ra.w & 0xffffu)), c1 = 2 * (abs(a - nb.c) + (int)(ra.w >> 16));
-                    const int c2 = 2 * (abs(a - nb.q) + (int)(rb.x & 0xffffu)), c3 = 2 * (abs(a - nb.b) + (int)(rb.x >> 16));
-                    const int c4 = abs(2 * a - e - nb.q) + (int)(rb.y & 0xffffu), c5 = abs(2 * a - nb.q - nb.c) + (int)(rb.y >> 16);
-                    const int c6 = abs(2 * a - nb.c - nb.b) + (int)(rb.z & 0xffffu);
-                    Pred pt;
-                    int best = c0;
-                    pt.ang2 = 2 * a;
-                    if (c1 < best) { best = c1; pt.ang2 = 2 * nb.b; }
-                    if (c2 < best) { best = c2; pt.ang2 = 2 * nb.c; }
-                    if (c3 < best) { best = c3; pt.ang2 = 2 * nb.d; }
-                    if (c4 < best) { best = c4; pt.ang2 = a + nb.c; }
-                    if (c5 < best) { best = c5; pt.ang2 = nb.c + nb.b; }
-                    if (c6 < best) { best = c6; pt.ang2 = nb.b + nb.d; }
-                    pt.spread = c0 + c1 + c2 + c3 + c4 + c5 + c6 - 7 * best;
-                    pt.lin16 = clampi(9 * a + (int)(rb.z >> 16) - 1024 - e, 0, 16 * 255);
-                    px0 = blend_prediction(pt, n_weight(pt.spread));
                 } else { /* first row: every neighbour falls back to the pixel on the left (R: NBLIC.c:288-303) */
                     const int a = j >= 1 ? x1 : 128;
                     nb.a = nb.b = nb.c = nb.d = nb.f = nb.g = nb.h = nb.q = nb.r = nb.s = nb.t = a;
                     nb.e = j >= 2 ? x2 : a;
-                    const Pred pt = predictor_terms(nb);
-                    px0 = blend_prediction(pt, n_weight(pt.spread));
+                }
+                int px0 = 0, ok1 = 0, ok2 = 0;
+                i64 p1 = 0, p2 = 0, ef0 = 0, r1 = 0, r2 = 0;
+                if constexpr (NAVP > 0) { /* R: NBLIC.c:831-846 */
+                    if (lane < NAVP) {
+                        const int sel = lane == 0 ? nb.a : lane == 1 ? nb.b : lane == 2 ? nb.c : lane == 3 ? nb.d : lane == 4 ? nb.e : lane == 5 ? nb.f :
+                                        lane == 6 ? nb.t : lane == 7 ? nb.h : lane == 8 ? nb.q : nb.g;
+                        avp_sm->vec[lane] = sel - 128;
+                    }
+                    r1 = ridge * 21 / 22; r2 = ridge * 22 / 21;
+                    r1 = clampl(r1, -1, ridge - 1); r2 = clampl(r2, ridge + 1, N_BIAS_MAX + 1);
+                    r1 = clampl(r1, 0, N_BIAS_MAX); r2 = clampl(r2, 0, N_BIAS_MAX);
+                    __syncwarp();
+                    avp_predict_pair<AN>(*avp_sm, E, Frow + (size_t)j * AM, r1, r2, lane, ok1, ok2, p1, p2, ef0);
+                    if (ok1) px0 = (int)((p1 + (1 << (N_FRAC - 1))) >> N_FRAC);
+                }
+                if (!ok1) { /* the 7-direction gradient predictor */
+                    if (i >= 1) {
+                        const int a = nb.a, e = nb.e;
+                        const int c0 = 2 * (abs(a - e) + (int)(ra.w & 0xffffu)), c1 = 2 * (abs(a - nb.c) + (int)(ra.w >> 16));
+                        const int c2 = 2 * (abs(a - nb.q) + (int)(rb.x & 0xffffu)), c3 = 2 * (abs(a - nb.b) + (int)(rb.x >> 16));
+                        const int c4 = abs(2 * a - e - nb.q) + (int)(rb.y & 0xffffu), c5 = abs(2 * a - nb.q - nb.c) + (int)(rb.y >> 16);
+                        const int c6 = abs(2 * a - nb.c - nb.b) + (int)(rb.z & 0xffffu);
+                        Pred pt;
+                        int best = c0;
+                        pt.ang2 = 2 * a;
+                        if (c1 < best) { best = c1; pt.ang2 = 2 * nb.b; }
+                        if (c2 < best) { best = c2; pt.ang2 = 2 * nb.c; }
+                        if (c3 < best) { best = c3; pt.ang2 = 2 * nb.d; }
+                        if (c4 < best) { best = c4; pt.ang2 = a + nb.c; }
+                        if (c5 < best) { best = c5; pt.ang2 = nb.c + nb.b; }
+                        if (c6 < best) { best = c6; pt.ang2 = nb.b + nb.d; }
+                        pt.spread = c0 + c1 + c2 + c3 + c4 + c5 + c6 - 7 * best;
+                        pt.lin16 = clampi(9 * a + (int)(rb.z >> 16) - 1024 - e, 0, 16 * 255);
+                        px0 = blend_prediction(pt, n_weight(pt.spread));
+                    } else {
+                        const Pred pt = predictor_terms(nb);
+                        px0 = blend_prediction(pt, n_weight(pt.spread));
+                    }
+                    p1 = (i64)px0 << N_FRAC;
                 }
                 const int act = i >= 1 ? abs(nb.a - nb.e) + abs(nb.a - nb.c) + (int)(ra.z >> 16) + 2 * abs(err) : activity(nb, err);
                 const u32 soft = sm.soft[min(act, 200)];
@@ -519,9 +556,15 @@ __device__ u32 coop_e1_feedback(const uint8_t *src, uint8_t *rec, int h, int w, 
                 err = clampi(x - px0, -127, 127);
                 if (lane == 0) sm.ctx[adr] = (int16_t)n_bias_learn(c, err);
                 x2 = x1; x1 = x;
+                if constexpr (NAVP > 0) { /* R: NBLIC.c:882-893 */
+                    const i64 target = (i64)x << N_FRAC;
+                    const i64 s_now = labs64(p1 - target);
+                    avp_learn_coop<AN>(*avp_sm, E, Brow + (size_t)j * AM, x, s_now, ef0 + s_now * 3 / 2, lane);
+                    if (ok1 && ok2) ridge = s_now > labs64(p2 - target) ? r2 : r1;
+                }
                 __syncwarp();
             }
-            if (lane < n_here) row[j0 + lane] = (uint8_t)my_x; /* one coalesced store per block */
+            if (out_rec && lane < n_here) out_rec[(size_t)i * w + j0 + lane] = (uint8_t)my_x; /* one coalesced store per block */
             __syncwarp();
         }
     }

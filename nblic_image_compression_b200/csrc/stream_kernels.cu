@@ -147,23 +147,32 @@ __global__ void __launch_bounds__(32) coder_kernel(Task *tasks, const int *order
     }
 }
 
-/* Warp-cooperative effort-1 kernels (coop_nblic.cuh): one warp per CTA, adaptive state in shared memory,
- * rank-mapper frequencies in `counts` (one [512][20] int table per CTA).
- * MODE 0: lossless encode (phase P = whole front end); 1: near-lossless encode; 2: decode. */
-template <int MODE>
-__global__ void __launch_bounds__(32) coop_e1_kernel(Task *tasks, const int *order, int n_order, int *queue, int *counts) {
+/* Warp-cooperative NBLIC kernels (coop_nblic.cuh, coop_avp.cuh): one warp per CTA, adaptive state in
+ * shared memory, rank-mapper frequencies in `counts` (one [512][20] int table per CTA), AVP column
+ * accumulators in `avp` (efforts 2 / 3: 2 * avp_half int64 per CTA).
+ * MODE 0: lossless effort-1 encode (phase P = whole front end); 1: encode with a per-pixel front end
+ * (near-lossless, and every effort-2/3 encode); 2: decode.  NAVP = 0 / 6 / 10 for effort 1 / 2 / 3. */
+template <int NAVP, int MODE>
+__global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *order, int n_order, int *queue, int *counts, i64 *avp,
+                                                        size_t avp_half) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x;
     int *my_counts = counts + (size_t)blockIdx.x * N_RANK_ENTRIES;
+    i64 *my_b = NAVP > 0 ? avp + (size_t)blockIdx.x * 2 * avp_half : nullptr;
     for (;;) {
         int pos = lane == 0 ? atomicAdd(queue, 1) : 0;
         pos = __shfl_sync(0xffffffffu, pos, 0);
         if (pos >= n_order) break;
         Task &t = tasks[order[pos]];
         u32 len;
-        if (MODE == 0) len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, *reinterpret_cast<CoopSmem *>(smem), my_counts, lane);
-        else len = coop_e1_feedback<MODE == 2>(t.src, t.rec, t.h, t.w, t.near, t.k_step, t.slot, t.slot_cap,
-                                               *reinterpret_cast<CoopSmemFeedback *>(smem), my_counts, lane);
+        if constexpr (MODE == 0) len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, *reinterpret_cast<CoopSmem *>(smem), my_counts, lane);
+        else {
+            AvpSmem *asm_ = NAVP > 0 ? &reinterpret_cast<CoopSmemAvp *>(smem)->avp : nullptr;
+            const bool lossless_enc = MODE == 1 && t.near == 0; /* neighbours are the source pixels themselves */
+            len = coop_feedback<NAVP, MODE == 2>(t.src, lossless_enc ? t.src : t.rec, lossless_enc ? nullptr : t.rec, t.h, t.w, t.near, t.k_step,
+                                                 t.slot, t.slot_cap, *reinterpret_cast<CoopSmemFeedback *>(smem), asm_, my_b,
+                                                 my_b ? my_b + avp_half : nullptr, my_counts, lane);
+        }
         if (lane == 0) {
             if (MODE == 2) { if (len != 0) t.status = NBLIC_B200_CORRUPT; }
             else {
@@ -174,6 +183,12 @@ __global__ void __launch_bounds__(32) coop_e1_kernel(Task *tasks, const int *ord
         }
         __syncwarp();
     }
+}
+
+/* test hook: the reciprocal-based exact division of coop_avp.cuh on arbitrary operands */
+__global__ void divcheck_kernel(const i64 *num, const i64 *den, int n, i64 *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = den[i] == 0 ? 0 : div_rcp(num[i], make_rcp(den[i]));
 }
 
 /* Exclusive scan of head_len + tail_len over the batch; one CTA of 1024 threads, warp shuffles. */
@@ -384,15 +399,22 @@ int launch_coder(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queu
     return launch_coder_t<KIND, DEC, MAP_LANE>(c, n_order, d_order, d_queue, plan, avp_stride);
 }
 
-template <int MODE>
-int launch_coop_e1(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue) {
-    const size_t smem = MODE == 0 ? sizeof(CoopSmem) : sizeof(CoopSmemFeedback);
+template <int NAVP, int MODE>
+int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w) {
+    const size_t smem = MODE == 0 ? sizeof(CoopSmem) : (NAVP > 0 ? sizeof(CoopSmemAvp) : sizeof(CoopSmemFeedback));
+    auto kern = coop_nblic_kernel<NAVP, MODE>;
     int per_sm = 0;
-    CK(cudaFuncSetAttribute(coop_e1_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_e1_kernel<MODE>, 32, smem));
-    const int grid = std::min(n_order, c->sm_count * std::max(per_sm, 1));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    int grid = std::min(n_order, c->sm_count * std::max(per_sm, 1));
+    size_t avp_half = 0;
+    if (NAVP > 0) { /* B and F: one m-vector per image column each; bound the grid by a 32 GB budget */
+        avp_half = (size_t)max_w * (1 + NAVP + NAVP * NAVP);
+        grid = (int)std::min<size_t>((size_t)grid, std::max<size_t>(((size_t)32 << 30) / (2 * avp_half * sizeof(i64)), 1));
+        CK(c->avp.reserve((size_t)grid * 2 * avp_half * sizeof(i64)));
+    }
     CK(c->coop_counts.reserve((size_t)grid * N_RANK_ENTRIES * sizeof(int)));
-    coop_e1_kernel<MODE><<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (int *)c->coop_counts.p);
+    kern<<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (int *)c->coop_counts.p, (i64 *)c->avp.p, avp_half);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -402,54 +424,57 @@ int launch_coop_e1(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_qu
 template <bool DEC>
 int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
     const int n = (int)tasks.size();
-    std::vector<int> order_q, order_n, order_c, order_f; /* QNBLIC, NBLIC sequential, NBLIC warp-cooperative (lossless encode / feedback) */
-    int max_w = 1, max_effort = 0;
+    /* launch groups: 0 QNBLIC, 1 NBLIC sequential kernels, 2 lossless effort-1 encode, 3..5 per-pixel front end, effort 1..3 */
+    enum { G_Q, G_SEQ, G_E1_LOSSLESS, G_FB1, G_FB2, G_FB3, N_GROUPS };
+    std::vector<int> group[N_GROUPS];
+    int max_w[N_GROUPS] = {1, 1, 1, 1, 1, 1}, seq_effort = 0;
     const bool coop_ok = c->mapping != NBLIC_B200_MAP_LANE && !c->serial_only;
     for (int i = 0; i < n; i++) {
-        if (tasks[i].status != NBLIC_B200_OK) continue;
-        if (tasks[i].effort == 0) { order_q.push_back(i); continue; }
-        if (coop_ok && tasks[i].effort == 1) { /* warp-cooperative kernels; lossless encodes first */
-            if (!DEC && tasks[i].near == 0) order_c.push_back(i); else order_f.push_back(i);
-            continue;
-        }
-        order_n.push_back(i);
-        max_w = std::max(max_w, tasks[i].w); max_effort = std::max(max_effort, tasks[i].effort);
+        const Task &t = tasks[(size_t)i];
+        if (t.status != NBLIC_B200_OK) continue;
+        int g;
+        if (t.effort == 0) g = G_Q;
+        else if (!coop_ok) { g = G_SEQ; seq_effort = std::max(seq_effort, t.effort); }
+        else if (!DEC && t.effort == 1 && t.near == 0) g = G_E1_LOSSLESS;
+        else g = G_FB1 + t.effort - 1;
+        group[g].push_back(i);
+        max_w[g] = std::max(max_w[g], t.w);
     }
     auto by_size = [&](int a, int b) {
-        const long long pa = (long long)tasks[a].h * tasks[a].w, pb = (long long)tasks[b].h * tasks[b].w;
+        const long long pa = (long long)tasks[(size_t)a].h * tasks[(size_t)a].w, pb = (long long)tasks[(size_t)b].h * tasks[(size_t)b].w;
         return pa != pb ? pa > pb : a < b;
     };
-    std::sort(order_q.begin(), order_q.end(), by_size);
-    std::sort(order_n.begin(), order_n.end(), by_size);
-    std::sort(order_c.begin(), order_c.end(), by_size);
-    std::sort(order_f.begin(), order_f.end(), by_size);
-
+    std::vector<int> order;
+    size_t start[N_GROUPS];
+    for (int g = 0; g < N_GROUPS; g++) {
+        std::sort(group[g].begin(), group[g].end(), by_size);
+        start[g] = order.size();
+        order.insert(order.end(), group[g].begin(), group[g].end());
+    }
     CK(c->tasks.reserve(sizeof(Task) * (size_t)std::max(n, 1)));
     CK(c->order.reserve(sizeof(int) * (size_t)std::max(n, 1)));
-    CK(c->queue.reserve(4 * sizeof(int)));
+    CK(c->queue.reserve(N_GROUPS * sizeof(int)));
     CK(cudaMemcpyAsync(c->tasks.p, tasks.data(), sizeof(Task) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    std::vector<int> order(order_q);
-    order.insert(order.end(), order_n.begin(), order_n.end());
-    order.insert(order.end(), order_c.begin(), order_c.end());
-    order.insert(order.end(), order_f.begin(), order_f.end());
     if (!order.empty()) CK(cudaMemcpyAsync(c->order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->queue.p, 0, 4 * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->queue.p, 0, N_GROUPS * sizeof(int), c->stream));
 
     CK(cudaEventRecord(c->ev0, c->stream));
-    if (!order_q.empty()) {
-        if (launch_coder<KIND_Q, DEC>(c, (int)order_q.size(), (const int *)c->order.p, (int *)c->queue.p, 1, 0)) return -1;
-    }
-    if (!order_n.empty()) {
-        if (launch_coder<KIND_N, DEC>(c, (int)order_n.size(), (const int *)c->order.p + order_q.size(), (int *)c->queue.p + 1, max_w, max_effort)) return -1;
-    }
-    if (!order_c.empty()) {
-        if (launch_coop_e1<0>(c, (int)order_c.size(), (const int *)c->order.p + order_q.size() + order_n.size(), (int *)c->queue.p + 2)) return -1;
-        c->last_map = "warp-coop";
-    }
-    if (!order_f.empty()) {
-        const int *d_ord = (const int *)c->order.p + order_q.size() + order_n.size() + order_c.size();
-        if (DEC ? launch_coop_e1<2>(c, (int)order_f.size(), d_ord, (int *)c->queue.p + 3) : launch_coop_e1<1>(c, (int)order_f.size(), d_ord, (int *)c->queue.p + 3)) return -1;
-        c->last_map = "warp-coop";
+    for (int g = 0; g < N_GROUPS; g++) {
+        if (group[g].empty()) continue;
+        const int cnt = (int)group[g].size();
+        const int *d_ord = (const int *)c->order.p + start[g];
+        int *d_q = (int *)c->queue.p + g;
+        int rc = 0;
+        switch (g) {
+            case G_Q: rc = launch_coder<KIND_Q, DEC>(c, cnt, d_ord, d_q, 1, 0); break;
+            case G_SEQ: rc = launch_coder<KIND_N, DEC>(c, cnt, d_ord, d_q, max_w[g], seq_effort); break;
+            case G_E1_LOSSLESS: rc = launch_coop<0, 0>(c, cnt, d_ord, d_q, max_w[g]); break;
+            case G_FB1: rc = launch_coop<0, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g]); break;
+            case G_FB2: rc = launch_coop<6, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g]); break;
+            case G_FB3: rc = launch_coop<10, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g]); break;
+        }
+        if (rc) return -1;
+        if (g >= G_E1_LOSSLESS) c->last_map = "warp-coop";
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     return 0;
@@ -750,6 +775,21 @@ int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *stre
     }
     CK(cudaStreamSynchronize(c->stream));
     return failed;
+}
+
+int nblic_b200_debug_divcheck(nblic_b200_ctx *c, const int64_t *num, const int64_t *den, int n, int64_t *out) {
+    if (!c || n < 0) return -1;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    CK(c->sym.reserve(3 * sizeof(i64) * (size_t)n));
+    i64 *d = (i64 *)c->sym.p;
+    CK(cudaMemcpyAsync(d, num, sizeof(i64) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + n, den, sizeof(i64) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    divcheck_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d, d + n, n, d + 2 * (size_t)n);
+    c->launches++;
+    CK(cudaMemcpyAsync(out, d + 2 * (size_t)n, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 int nblic_b200_synth_gray(nblic_b200_ctx *c, uint8_t *d_out, int height, int width, uint32_t seed, const int32_t *occluders) {

@@ -107,6 +107,33 @@ def test_avp_on_kodak_crops_and_synth(api, codec, oracle, kodak, effort, near):
     _check_batch(api, codec, oracle, images, effort, near, api.MAP_WARP)
 
 
+def test_exact_int64_division(codec):
+    """The AVP kernels divide by a per-step reciprocal (estimate, multiply back, correct): must equal C's
+    truncating int64 division for every operand pair, including magnitudes beyond 2^53."""
+    rng = np.random.default_rng(7)
+    nums, dens = [], []
+    for bits_n in (1, 8, 20, 33, 47, 52, 53, 54, 60, 62, 63):
+        for bits_d in (1, 5, 13, 17, 31, 40, 52, 53, 60, 61, 62, 63):
+            n = rng.integers(0, 1 << bits_n, size=400, dtype=np.uint64).astype(np.int64)
+            d = rng.integers(1, max(2, 1 << bits_d), size=400, dtype=np.uint64).astype(np.int64)
+            sn = rng.integers(0, 2, size=400) * 2 - 1
+            sd = rng.integers(0, 2, size=400) * 2 - 1
+            nums.append(n * sn); dens.append(np.where(d == 0, 1, d) * sd)
+    edge = np.array([0, 1, -1, 2, -2, 3, 2**53 - 1, 2**53, 2**53 + 1, -(2**53) - 1, 2**62, -(2**62), 2**63 - 1, -(2**63) + 1, 4096, 65536, 65535], dtype=np.int64)
+    nums.append(np.repeat(edge, len(edge))); dens.append(np.tile(np.where(edge == 0, 7, edge), len(edge)))
+    # near-multiples: n = q*d + r with r in {-1, 0, 1, d-1}
+    q = rng.integers(0, 1 << 40, size=4000, dtype=np.int64); d = rng.integers(1, 1 << 22, size=4000, dtype=np.int64)
+    for r in (-1, 0, 1):
+        nums.append(q * d + r); dens.append(d)
+    nums.append(q * d + d - 1); dens.append(d)
+    num, den = np.concatenate(nums), np.concatenate(dens)
+    got = codec.divcheck(num, den)
+    exp = np.array([int(abs(int(a)) // abs(int(b))) * (1 if (a < 0) == (b < 0) else -1) for a, b in zip(num.tolist(), den.tolist())], dtype=object)
+    exp = np.array([((int(v) + 2**63) % 2**64) - 2**63 for v in exp], dtype=np.int64)
+    bad = np.nonzero(got != exp)[0]
+    assert len(bad) == 0, (num[bad[:5]], den[bad[:5]], got[bad[:5]], exp[bad[:5]])
+
+
 def test_synthetic_golden_streams(api, codec, manifest):
     for key in ("64x64_s0", "200x333_s7", "1024x1024_s0"):
         h, w, s = int(key.split("x")[0]), int(key.split("x")[1].split("_")[0]), int(key.split("_s")[1])
