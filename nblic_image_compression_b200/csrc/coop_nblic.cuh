@@ -42,12 +42,14 @@ struct __align__(16) PixRec {
     u32 orig;   /* encoder: the original pixel                                                */
 };
 
-/* shared-memory image of one stream's adaptive state (one warp = one CTA) */
+/* shared-memory image of one stream's adaptive state (one warp = one CTA).  The counter forest follows
+ * as a separate, compacted array: class u only owns the (256 >> top) << (u / k_step) nodes its Golomb
+ * order can reach (1000 nodes = 4 KB for lossless streams instead of 16 x 256). */
 struct CoopSmem {
-    u32 forest[N_FOREST_ENTRIES];      /* 16 KB: node counters n0 | n1 << 16                          */
     int16_t ctx[N_CTX_ENTRIES];        /*  4 KB: bias-cancel table                                    */
     uint8_t rank[N_RANK_ENTRIES];      /* 10 KB: encoder: symbol -> rank; decoder: rank -> symbol       */
     uint16_t soft[208];                /* activity (clamped to 200) -> u | v << 4 | wv << 8             */
+    uint16_t fbase[N_CLASSES];         /* first forest slot of class u                                 */
 };
 /* the feedback modes add the phase-P records of the current block */
 struct CoopSmemFeedback {
@@ -59,6 +61,16 @@ struct CoopSmemAvp {
     CoopSmemFeedback fb;
     AvpSmem avp;
 };
+
+/* number of forest nodes a stream with this k_step can touch (host and device) */
+__host__ __device__ inline int forest_nodes(int k_step) {
+    const int top = (N_CLASSES - 1) / k_step;
+    int n = 0;
+    for (int u = 0; u < N_CLASSES; u++) n += (256 >> top) << (u / k_step);
+    return n;
+}
+/* slot of tree node `node` inside a class of order k: unary index and in-order suffix offset */
+NB_DEV int compact_node(int node, int top, int k) { return ((node >> top) << k) + (node & ((1 << k) - 1)); }
 
 /* ---- byte streams: a 128-byte line lives in the warp, one 32-bit word per lane ---------------- */
 
@@ -137,13 +149,23 @@ NB_DEV u32 learn_packed(u32 c, int bit, int weight) { /* node_learn on the packe
     if ((c & 0xffffu) + (c >> 16) > (u32)(N_MIX * 256)) c = ((c + 0x00010001u) >> 1) & 0x7fff7fffu;
     return c;
 }
+/* floor(4096 * n1 / (n0 + n1)) without the integer divide: float estimate (error < 2e-3), multiply back,
+ * correct by one.  n0 + n1 <= 8224 and 4096 * n1 < 2^26 with 12 trailing zero bits, so both convert exactly. */
+NB_DEV int node_p1_fast(u32 packed) {
+    const u32 n1 = packed >> 16, s = (packed & 0xffffu) + n1, a = n1 << 12;
+    u32 q = __float2uint_rz(__fdividef(__uint2float_rn(a), __uint2float_rn(s)));
+    const int r = (int)a - (int)(q * s);
+    if (r < 0) q--; else if (r >= (int)s) q++;
+    return (int)q;
+}
 NB_DEV u32 mixed_p(u32 cu, u32 cv, int wv) { /* R: NBLIC.c:627-631 */
-    const int p = (node_p1(cu) * (N_MIX - wv) + node_p1(cv) * wv + N_MIX / 2) >> 5; /* operands >= 0: >> 5 == / 32 */
+    const int p = (node_p1_fast(cu) * (N_MIX - wv) + node_p1_fast(cv) * wv + N_MIX / 2) >> 5; /* operands >= 0: >> 5 == / 32 */
     return (u32)clampi(p, 1, N_PROB_ONE - 1);
 }
-NB_DEV void learn_pair(u32 *forest, int u, int v, int node, u32 cu, u32 cv, int wv, int bit) {
-    if (u == v) forest[u * 256 + node] = learn_packed(learn_packed(cu, bit, N_MIX - wv), bit, wv);
-    else { forest[u * 256 + node] = learn_packed(cu, bit, N_MIX - wv); forest[v * 256 + node] = learn_packed(cv, bit, wv); }
+/* iu / iv: forest slots of the node in the main and the side class (equal when both are the same class) */
+NB_DEV void learn_pair(u32 *forest, int iu, int iv, u32 cu, u32 cv, int wv, int bit) {
+    if (iu == iv) forest[iu] = learn_packed(learn_packed(cu, bit, N_MIX - wv), bit, wv);
+    else { forest[iu] = learn_packed(cu, bit, N_MIX - wv); forest[iv] = learn_packed(cv, bit, wv); }
 }
 
 /* k = u / k_step for u = 0..15, 4 bits each */
@@ -154,8 +176,10 @@ NB_DEV unsigned long long make_order_table(int k_step) {
 }
 NB_DEV int order_of(unsigned long long tab, int u) { return (int)((tab >> (4 * u)) & 15u); }
 
-NB_DEV void coop_reset(CoopSmem &sm, int *count, int lane) {
-    for (int k = lane; k < N_FOREST_ENTRIES; k += 32) sm.forest[k] = (u32)N_MIX | ((u32)N_MIX << 16);
+NB_DEV void coop_reset(CoopSmem &sm, u32 *forest, int k_step, int *count, int lane) {
+    const int n_nodes = forest_nodes(k_step), top = (N_CLASSES - 1) / k_step;
+    for (int k = lane; k < n_nodes; k += 32) forest[k] = (u32)N_MIX | ((u32)N_MIX << 16);
+    if (lane < N_CLASSES) { int b = 0; for (int u = 0; u < lane; u++) b += (256 >> top) << (u / k_step); sm.fbase[lane] = (uint16_t)b; }
     for (int k = lane; k < N_CTX_ENTRIES; k += 32) sm.ctx[k] = 0;
     for (int k = lane; k < N_RANK_ENTRIES; k += 32) { const int r = k % N_RANKS; sm.rank[k] = (uint8_t)r; count[k] = 2 * (N_RANKS - 1 - r); }
     for (int d = lane; d <= 200; d += 32) { int u, v, wv; n_soft_class(d, u, v, wv); sm.soft[d] = (uint16_t)(u | (v << 4) | (wv << 8)); }
@@ -170,49 +194,55 @@ NB_DEV void coop_put_header(CoopCoder<false> &rc, int h, int w, int near, int k_
 }
 
 /* ---- encoder side of one symbol: every decision of the pixel in its own lane ------------------- */
-NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, int k_step, int top, unsigned long long ktab, int u, int v, int wv, int z,
-                               int lane) {
+NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, u32 *forest, int k_step, int top, unsigned long long ktab, int u, int v, int wv,
+                               int z, int lane) {
     const int k = order_of(ktab, u);
     if (order_of(ktab, v) != k) v = u;
+    const int bu = sm.fbase[u], bv = sm.fbase[v];
     const int q = z >> k;
     const int D = q + 1 + k; /* decisions of this pixel */
     if (q < (256 >> top) && D <= 32) {
-        int node, bit;
-        if (lane <= q) { node = lane << top; bit = lane < q; }          /* unary run, then its terminating 0 */
+        int slot, bit; /* slot = compacted node index inside the class */
+        if (lane <= q) { slot = lane << k; bit = lane < q; }             /* unary run, then its terminating 0 */
         else {
             const int t = lane - q - 1, kk = max(k - 1 - t, 0);          /* t-th suffix bit, weight 2^kk */
             const int hi_bits = (z & ((1 << k) - 1)) & ~((2 << kk) - 1);
-            node = ((q << top) + 1 + hi_bits + t - __popc(hi_bits)) & 255;
+            slot = (q << k) + ((1 + hi_bits + t - __popc(hi_bits)) & ((1 << k) - 1));
             bit = (z >> kk) & 1;
         }
         u32 coded = 0;
         if (lane < D) {
-            const u32 cu = sm.forest[u * 256 + node], cv = sm.forest[v * 256 + node];
+            const u32 cu = forest[bu + slot], cv = forest[bv + slot];
             coded = mixed_p(cu, cv, wv) | ((u32)bit << 12);
-            learn_pair(sm.forest, u, v, node, cu, cv, wv, bit);
+            learn_pair(forest, bu + slot, bv + slot, cu, cv, wv, bit);
         }
         for (int d = 0; d < D; d++) {
             const u32 cd = __shfl_sync(FULL, coded, d);
             rc.bit((int)(cd >> 12), cd & 0xfffu);
         }
-    } else { /* order escape (or an over-long unary run): sequential routine, bits replayed through the warp coder */
-        /* The leader walks the decisions in order; each (bit, p) is broadcast so every lane's coder stays in step. */
-        const int n_top = (N_CLASSES - 1) / k_step;
-        int node = 0, kk = k, uu = u, vv = v, phase = 0; /* phase 0: unary, 1: suffix, 2: done */
+    } else { /* order escape (or an over-long unary run): the decisions one after the other, warp-uniform */
+        int node = 0, kk = k, iu_base = bu, iv_base = bv, phase = 0; /* phase 0: unary, 1: suffix, 2: done */
+        int k_tree = k;                                             /* order of the tree being walked */
         while (phase < 2) {
             int bit;
-            if (phase == 0) bit = (node >> n_top) < (z >> kk);
+            if (phase == 0) bit = (node >> top) < (z >> kk);
             else bit = (z >> kk) & 1;
-            const u32 cu = sm.forest[uu * 256 + node], cv = sm.forest[vv * 256 + node];
+            const int slot = compact_node(node, top, k_tree);
+            const u32 cu = forest[iu_base + slot], cv = forest[iv_base + slot];
             rc.bit(bit, mixed_p(cu, cv, wv));
             __syncwarp();
-            if (lane == 0) learn_pair(sm.forest, uu, vv, node, cu, cv, wv, bit);
+            if (lane == 0) learn_pair(forest, iu_base + slot, iv_base + slot, cu, cv, wv, bit);
             __syncwarp();
             if (phase == 0) {
                 if (!bit) { node++; kk--; phase = kk >= 0 ? 1 : 2; }
                 else {
-                    node += 1 << n_top;
-                    if (node >= 256) { node >>= 1; uu = vv = (kk + 1) * k_step; kk = uu / k_step; if (uu >= N_CLASSES) { rc.out.overflow = true; phase = 2; } }
+                    node += 1 << top;
+                    if (node >= 256) { /* escape to the next order (R: NBLIC.c:658-662) */
+                        node >>= 1;
+                        const int uu = (kk + 1) * k_step;
+                        if (uu >= N_CLASSES) { rc.out.overflow = true; phase = 2; }
+                        else { kk = order_of(ktab, uu); k_tree = kk; iu_base = iv_base = sm.fbase[uu]; }
+                    }
                 }
             } else {
                 node += bit ? (1 << kk) : 1;
@@ -225,16 +255,18 @@ NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, int k_step, i
 
 /* ---- decoder side of one symbol ----------------------------------------------------------------- */
 /* Returns z, or -1 for a corrupt stream. */
-NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, int k_step, int top, unsigned long long ktab, int u, int v, int wv, int lane) {
+NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, int k_step, int top, unsigned long long ktab, int u, int v, int wv,
+                              int lane) {
     int k = order_of(ktab, u);
     if (order_of(ktab, v) != k) v = u;
+    const int bu = sm.fbase[u], bv = sm.fbase[v];
     const int n_unary = 256 >> top; /* unary nodes of one tree before the order escape */
     int q = -1;
     for (int base = 0; base < n_unary && q < 0; base += 32) {
         /* every lane evaluates one candidate node of the unary run */
-        const int d = base + lane, node = (d << top) & 255;
+        const int d = base + lane, slot = d << k;
         u32 cu = 0, cv = 0, p = 0;
-        if (d < n_unary) { cu = sm.forest[u * 256 + node]; cv = sm.forest[v * 256 + node]; p = mixed_p(cu, cv, wv); }
+        if (d < n_unary) { cu = forest[bu + slot]; cv = forest[bv + slot]; p = mixed_p(cu, cv, wv); }
         const int lim = min(32, n_unary - base);
         int stop = -1;
         for (int dd = 0; dd < lim; dd++) {
@@ -242,31 +274,33 @@ NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, int k_step, int
             if (!rc.bit(0, pd)) { stop = dd; break; }
         }
         const int last = stop >= 0 ? stop : lim - 1;
-        if (lane <= last) learn_pair(sm.forest, u, v, node, cu, cv, wv, !(stop >= 0 && lane == stop));
+        if (lane <= last) learn_pair(forest, bu + slot, bv + slot, cu, cv, wv, !(stop >= 0 && lane == stop));
         if (stop >= 0) q = base + stop;
     }
     __syncwarp();
-    if (q < 0) { /* order escape: continue sequentially in the next order's tree (R: NBLIC.c:658-662) */
+    if (q < 0) { /* order escape: continue one decision at a time in the next order's tree (R: NBLIC.c:658-662) */
         int uu = (k + 1) * k_step, node = 128;
         for (;;) {
             if (uu >= N_CLASSES) return -1;
-            k = uu / k_step;
-            const u32 c = sm.forest[uu * 256 + node];
+            k = order_of(ktab, uu);
+            const int at = sm.fbase[uu] + compact_node(node, top, k);
+            const u32 c = forest[at];
             const int bit = rc.bit(0, mixed_p(c, c, wv));
             __syncwarp();
-            if (lane == 0) learn_pair(sm.forest, uu, uu, node, c, c, wv, bit);
+            if (lane == 0) learn_pair(forest, at, at, c, c, wv, bit);
             __syncwarp();
             if (!bit) break;
             node += 1 << top;
             if (node >= 256) { node >>= 1; uu = (k + 1) * k_step; }
         }
         int z = (node >> top) << k;
+        const int k_tree = k;
         for (node++, k--; k >= 0; k--) {
-            const int at = node & 255;
-            const u32 c = sm.forest[uu * 256 + at];
+            const int at = sm.fbase[uu] + compact_node(node & 255, top, k_tree);
+            const u32 c = forest[at];
             const int bit = rc.bit(0, mixed_p(c, c, wv));
             __syncwarp();
-            if (lane == 0) learn_pair(sm.forest, uu, uu, at, c, c, wv, bit);
+            if (lane == 0) learn_pair(forest, at, at, c, c, wv, bit);
             __syncwarp();
             if (bit) z += 1 << k;
             node += bit ? (1 << k) : 1;
@@ -277,25 +311,29 @@ NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, int k_step, int
     if (k > 0) { /* suffix: lane L in [1, 2^k) is the node reached by the bit prefix spelled by L below its leading 1 */
         const int L = max(lane, 1), t = 31 - __clz(L), prefix = L ^ (1 << t);
         const bool valid = lane >= 1 && lane < (1 << k);
-        const int node = ((q << top) + 1 + (prefix << max(k - t, 0)) + t - __popc(prefix)) & 255;
+        const int slot = (q << k) + ((1 + (prefix << max(k - t, 0)) + t - __popc(prefix)) & ((1 << k) - 1));
         u32 cu = 0, cv = 0, p = 0;
-        if (valid) { cu = sm.forest[u * 256 + node]; cv = sm.forest[v * 256 + node]; p = mixed_p(cu, cv, wv); }
+        if (valid) { cu = forest[bu + slot]; cv = forest[bv + slot]; p = mixed_p(cu, cv, wv); }
         int cur = 1;
         for (int s = 0; s < k; s++) {
             const u32 pd = __shfl_sync(FULL, p, cur);
             cur = 2 * cur + rc.bit(0, pd);
         }
         z += cur - (1 << k);
-        if (valid && (cur >> (k - t)) == lane) learn_pair(sm.forest, u, v, node, cu, cv, wv, (cur >> (k - t - 1)) & 1);
+        if (valid && (cur >> (k - t)) == lane) learn_pair(forest, bu + slot, bv + slot, cu, cv, wv, (cur >> (k - t - 1)) & 1);
     }
     return z;
 }
 
 /* ---- rank mapper, lane s holds entry s of the key's table ---------------------------------------- */
-/* encoder: table = symbol -> rank.  Returns z. */
-NB_DEV int coop_rank_encode(CoopSmem &sm, int *count, int key, int y, int lane, int &my_rank, int &my_count) {
-    my_rank = lane < N_RANKS ? (int)sm.rank[key + lane] : 255;
+/* Both directions first fetch the key's 20 table entries and frequencies (lane s < 20 holds entry s);
+ * the frequencies live in global memory (L2), so the fetch is issued before the symbol is coded. */
+NB_DEV void coop_rank_fetch(const CoopSmem &sm, const int *count, int key, int lane, int &my_tab, int &my_count) {
+    my_tab = lane < N_RANKS ? (int)sm.rank[key + lane] : 255;
     my_count = lane < N_RANKS ? __ldcg(count + key + lane) : 0;
+}
+/* encoder: table = symbol -> rank */
+NB_DEV int coop_rank_encode(int y, int my_rank) {
     const int zr = __shfl_sync(FULL, my_rank, y & 31);
     return y < N_RANKS ? zr : y;
 }
@@ -313,10 +351,8 @@ NB_DEV void coop_rank_touch_encode(CoopSmem &sm, int *count, int key, int y, int
     }
 }
 /* decoder: table = rank -> symbol.  Returns y and performs the update. */
-NB_DEV int coop_rank_decode(CoopSmem &sm, int *count, int key, int z, int lane) {
+NB_DEV int coop_rank_decode(CoopSmem &sm, int *count, int key, int z, int lane, int my_sym, int my_count) {
     if (z >= N_RANKS) return z;
-    const int my_sym = lane < N_RANKS ? (int)sm.rank[key + lane] : 255;
-    const int my_count = lane < N_RANKS ? __ldcg(count + key + lane) : 0;
     const int y = __shfl_sync(FULL, my_sym, z);
     const int other = __shfl_sync(FULL, my_sym, max(z - 1, 0));
     const int cz = __shfl_sync(FULL, my_count, z) + 1;
@@ -335,10 +371,11 @@ NB_DEV int coop_rank_decode(CoopSmem &sm, int *count, int key, int z, int lane) 
  * `count`: the stream's rank-mapper frequency table in global memory ([512][20] int, indexed by rank).
  * `stream` must be 128-byte aligned.  Returns the stream length or 0xffffffff on overflow.
  */
-__device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, int *count, int lane) {
+__device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, u32 *forest, int *count,
+                                        int lane) {
     const int k_step = 3, top = (N_CLASSES - 1) / k_step; /* near = 0 (R: NBLIC.c:769) */
     const unsigned long long ktab = make_order_table(k_step);
-    coop_reset(sm, count, lane);
+    coop_reset(sm, forest, k_step, count, lane);
     CoopCoder<false> rc;
     rc.out.start(stream, cap, lane);
     coop_put_header(rc, h, w, 0, k_step, 1);
@@ -380,8 +417,9 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
 
                 const int key = ((px << 1) | sign) * N_RANKS;
                 int my_rank, my_count;
-                const int z = coop_rank_encode(sm, count, key, y, lane, my_rank, my_count);
-                coop_encode_symbol(rc, sm, k_step, top, ktab, u, v, wv, z, lane);
+                coop_rank_fetch(sm, count, key, lane, my_rank, my_count);
+                const int z = coop_rank_encode(y, my_rank);
+                coop_encode_symbol(rc, sm, forest, k_step, top, ktab, u, v, wv, z, lane);
                 coop_rank_touch_encode(sm, count, key, y, z, lane, my_rank, my_count);
                 __syncwarp();
             }
@@ -401,7 +439,7 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
  */
 template <int NAVP, bool DEC>
 __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *out_rec, int h, int w, int near, int k_step, uint8_t *stream,
-                             u32 cap, CoopSmemFeedback &smf, AvpSmem *avp_sm, i64 *Brow, i64 *Frow, int *count, int lane) {
+                             u32 cap, CoopSmemFeedback &smf, AvpSmem *avp_sm, u32 *forest, i64 *Brow, i64 *Frow, int *count, int lane) {
     CoopSmem &sm = smf.st;
     constexpr int AN = NAVP > 0 ? NAVP : 1;
     constexpr int AM = AvpGeom<AN>::M, ANS = AvpGeom<AN>::NS;
@@ -409,7 +447,7 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
     const unsigned long long ktab = make_order_table(k_step);
     const int qn = 2 * near + 1;
     const u32 qmagic = 65536u / (u32)qn + 1u; /* n / qn == (n * qmagic) >> 16 for 0 <= n < 3400 */
-    coop_reset(sm, count, lane);
+    coop_reset(sm, forest, k_step, count, lane);
     i64 E[ANS], ridge = 8;
     if constexpr (NAVP > 0) {
         for (size_t k = lane; k < (size_t)w * AM; k += 32) Brow[k] = 0;
@@ -530,19 +568,19 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
                 const int key = ((px << 1) | sign) * N_RANKS;
                 const int room = (int)(((u32)(min(px, 255 - px) + near) * qmagic) >> 16);
 
-                int y;
+                int y, my_tab, my_count;
+                coop_rank_fetch(sm, count, key, lane, my_tab, my_count);
                 if constexpr (DEC) {
-                    const int z = coop_decode_symbol(rc, sm, k_step, top, ktab, u, v, wv, lane);
+                    const int z = coop_decode_symbol(rc, sm, forest, k_step, top, ktab, u, v, wv, lane);
                     if (z < 0) return 1u;
-                    y = coop_rank_decode(sm, count, key, z, lane);
+                    y = coop_rank_decode(sm, count, key, z, lane, my_tab, my_count);
                 } else {
                     const int xo = (int)rb.w;
                     const int mag = (int)(((u32)(abs(xo - px) + near) * qmagic) >> 16);
                     y = mag <= 0 ? 0 : (mag <= room ? 2 * mag - ((xo >= px) ^ sign) : mag + room);
-                    int my_rank, my_count;
-                    const int z = coop_rank_encode(sm, count, key, y, lane, my_rank, my_count);
-                    coop_encode_symbol(rc, sm, k_step, top, ktab, u, v, wv, z, lane);
-                    coop_rank_touch_encode(sm, count, key, y, z, lane, my_rank, my_count);
+                    const int z = coop_rank_encode(y, my_tab);
+                    coop_encode_symbol(rc, sm, forest, k_step, top, ktab, u, v, wv, z, lane);
+                    coop_rank_touch_encode(sm, count, key, y, z, lane, my_tab, my_count);
                 }
 
                 /* reconstruction (R: NBLIC.c:449-466) */

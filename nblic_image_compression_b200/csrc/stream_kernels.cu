@@ -165,12 +165,14 @@ __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *
         if (pos >= n_order) break;
         Task &t = tasks[order[pos]];
         u32 len;
-        if constexpr (MODE == 0) len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, *reinterpret_cast<CoopSmem *>(smem), my_counts, lane);
+        constexpr size_t fixed = MODE == 0 ? sizeof(CoopSmem) : (NAVP > 0 ? sizeof(CoopSmemAvp) : sizeof(CoopSmemFeedback));
+        u32 *forest = reinterpret_cast<u32 *>(smem + ((fixed + 15) & ~(size_t)15)); /* sized by the host for the largest k_step of the launch */
+        if constexpr (MODE == 0) len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, *reinterpret_cast<CoopSmem *>(smem), forest, my_counts, lane);
         else {
             AvpSmem *asm_ = NAVP > 0 ? &reinterpret_cast<CoopSmemAvp *>(smem)->avp : nullptr;
             const bool lossless_enc = MODE == 1 && t.near == 0; /* neighbours are the source pixels themselves */
             len = coop_feedback<NAVP, MODE == 2>(t.src, lossless_enc ? t.src : t.rec, lossless_enc ? nullptr : t.rec, t.h, t.w, t.near, t.k_step,
-                                                 t.slot, t.slot_cap, *reinterpret_cast<CoopSmemFeedback *>(smem), asm_, my_b,
+                                                 t.slot, t.slot_cap, *reinterpret_cast<CoopSmemFeedback *>(smem), asm_, forest, my_b,
                                                  my_b ? my_b + avp_half : nullptr, my_counts, lane);
         }
         if (lane == 0) {
@@ -400,8 +402,9 @@ int launch_coder(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queu
 }
 
 template <int NAVP, int MODE>
-int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w) {
-    const size_t smem = MODE == 0 ? sizeof(CoopSmem) : (NAVP > 0 ? sizeof(CoopSmemAvp) : sizeof(CoopSmemFeedback));
+int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w, int max_nodes) {
+    const size_t fixed = MODE == 0 ? sizeof(CoopSmem) : (NAVP > 0 ? sizeof(CoopSmemAvp) : sizeof(CoopSmemFeedback));
+    const size_t smem = ((fixed + 15) & ~(size_t)15) + sizeof(u32) * (size_t)max_nodes; /* fixed tables + the compacted counter forest */
     auto kern = coop_nblic_kernel<NAVP, MODE>;
     int per_sm = 0;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -427,7 +430,7 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
     /* launch groups: 0 QNBLIC, 1 NBLIC sequential kernels, 2 lossless effort-1 encode, 3..5 per-pixel front end, effort 1..3 */
     enum { G_Q, G_SEQ, G_E1_LOSSLESS, G_FB1, G_FB2, G_FB3, N_GROUPS };
     std::vector<int> group[N_GROUPS];
-    int max_w[N_GROUPS] = {1, 1, 1, 1, 1, 1}, seq_effort = 0;
+    int max_w[N_GROUPS] = {1, 1, 1, 1, 1, 1}, max_nodes[N_GROUPS] = {0, 0, 0, 0, 0, 0}, seq_effort = 0;
     const bool coop_ok = c->mapping != NBLIC_B200_MAP_LANE && !c->serial_only;
     for (int i = 0; i < n; i++) {
         const Task &t = tasks[(size_t)i];
@@ -439,6 +442,7 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
         else g = G_FB1 + t.effort - 1;
         group[g].push_back(i);
         max_w[g] = std::max(max_w[g], t.w);
+        if (t.effort > 0) max_nodes[g] = std::max(max_nodes[g], forest_nodes(t.k_step));
     }
     auto by_size = [&](int a, int b) {
         const long long pa = (long long)tasks[(size_t)a].h * tasks[(size_t)a].w, pb = (long long)tasks[(size_t)b].h * tasks[(size_t)b].w;
@@ -468,10 +472,10 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
         switch (g) {
             case G_Q: rc = launch_coder<KIND_Q, DEC>(c, cnt, d_ord, d_q, 1, 0); break;
             case G_SEQ: rc = launch_coder<KIND_N, DEC>(c, cnt, d_ord, d_q, max_w[g], seq_effort); break;
-            case G_E1_LOSSLESS: rc = launch_coop<0, 0>(c, cnt, d_ord, d_q, max_w[g]); break;
-            case G_FB1: rc = launch_coop<0, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g]); break;
-            case G_FB2: rc = launch_coop<6, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g]); break;
-            case G_FB3: rc = launch_coop<10, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g]); break;
+            case G_E1_LOSSLESS: rc = launch_coop<0, 0>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
+            case G_FB1: rc = launch_coop<0, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
+            case G_FB2: rc = launch_coop<6, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
+            case G_FB3: rc = launch_coop<10, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
         }
         if (rc) return -1;
         if (g >= G_E1_LOSSLESS) c->last_map = "warp-coop";

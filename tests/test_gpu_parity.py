@@ -100,6 +100,29 @@ def test_kodak_near_lossless_e1_golden(api, codec, kodak, manifest, key):
         assert np.array_equal(d[0], r)
 
 
+@pytest.mark.parametrize("key", ["e2n0", "e2n1", "e2n2", "e2n3", "e3n0", "e3n1", "e3n2", "e3n3"])
+def test_kodak_avp_golden(api, codec, kodak, manifest, key):
+    """configs[3] (Kodak part) and the effort-2/3 rows of BASELINE.md section 4: all 24 images, bytes,
+    reconstruction and decode against the unmodified reference's manifest."""
+    effort, near = int(key[1]), int(key[3])
+    names = sorted(kodak)
+    codec.set_mapping(api.MAP_AUTO)
+    streams, recs, status = codec.encode_batch([kodak[n] for n in names], near, effort, want_recon=near > 0)
+    assert all(s == api.OK for s in status)
+    total = 0
+    for n, s, r in zip(names, streams, recs):
+        ent = manifest["kodak"][n]["streams"][key]
+        assert len(s) == ent["bytes"] and sha(s) == ent["sha256"], (n, key)
+        total += len(s)
+        if near:
+            assert sha(r.tobytes()) == ent["recon_sha256"], (n, key)
+    assert total == {"e2n0": 4822520, "e2n1": 3131838, "e2n2": 2395034, "e2n3": 1946717,
+                     "e3n0": 4795969, "e3n1": 3107665, "e3n2": 2372893, "e3n3": 1928846}[key]  # BASELINE.md section 4
+    for n, d, r in zip(names, codec.decode_batch(streams), recs):
+        assert d is not None and np.array_equal(d[0], r if near else kodak[n]), (n, key)
+        assert (d[1], d[2]) == (near, effort)
+
+
 @pytest.mark.parametrize("effort,near", [(2, 0), (2, 2), (3, 0), (3, 1)])
 def test_avp_on_kodak_crops_and_synth(api, codec, oracle, kodak, effort, near):
     """-e2 / -e3 (int64 least-squares predictor) on crops: the oracle needs seconds per Kodak-size image."""
@@ -140,8 +163,6 @@ def test_synthetic_golden_streams(api, codec, manifest):
         img = gen(h, w, s)
         for skey, ent in manifest["synthetic"][key]["streams"].items():
             effort, near = int(skey[1]), int(skey[3])
-            if effort >= 2 and h * w > 100_000:
-                continue  # full-size AVP streams are covered by the round-trip property test
             streams, _, _ = codec.encode_batch([img], near, effort)
             assert len(streams[0]) == ent["bytes"] and sha(streams[0]) == ent["sha256"], (key, skey)
 
