@@ -197,6 +197,30 @@ def test_legacy_entry_points(api, oracle, kodak):
     assert api.legacy.nblic_compress(np.zeros((0, 5), np.uint8), 0, 1)[0] is None
 
 
+def test_dropin_cli_matches_reference_cli(tmp_path, kodak, manifest):
+    """The reference's own unmodified CLI (src/NBLIC_main.c + src/FileIO.c) linked against libnblic_b200.so
+    (oracle/Makefile `dropin`) produces the same .nblic files and the same decoded PGMs as the reference CLI."""
+    import subprocess
+    from conftest import ROOT
+    ours = os.path.join(ROOT, "oracle", "_ref", "nblic_codec_b200")
+    theirs = os.path.join(ROOT, "oracle", "_ref", "nblic_codec_ref")
+    if not (os.path.exists(ours) and os.path.exists(theirs)):
+        pytest.skip("drop-in binaries not built (reference tree was absent at build time)")
+    img = kodak["01"]
+    pgm = tmp_path / "k01.pgm"
+    pgm.write_bytes(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]) + img.tobytes())
+    for switches, key in (("-cn0e0", "e0n0"), ("-ctn0e0", "e0n0"), ("-cn0e1", "e1n0"), ("-cn2e2", "e2n2")):
+        a, b = tmp_path / f"a{key}.nblic", tmp_path / f"b{key}.nblic"
+        subprocess.run([ours, switches, str(pgm), str(a)], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([theirs, switches, str(pgm), str(b)], check=True, stdout=subprocess.DEVNULL)
+        assert a.read_bytes() == b.read_bytes(), switches
+        assert sha(a.read_bytes()) == manifest["kodak"]["01"]["streams"][key]["sha256"]
+        da, db = tmp_path / f"a{key}.pgm", tmp_path / f"b{key}.pgm"
+        subprocess.run([ours, "-d", str(a), str(da)], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([theirs, "-d", str(b), str(db)], check=True, stdout=subprocess.DEVNULL)
+        assert da.read_bytes() == db.read_bytes(), switches
+
+
 def test_bad_and_ragged_inputs(api, codec):
     good = codec.encode_batch([gen(8, 8, 1)], 0, 1)[0][0]
     hdr = bytearray(good); hdr[15] = 4
