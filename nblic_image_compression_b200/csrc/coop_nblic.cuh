@@ -42,6 +42,60 @@ struct __align__(16) PixRec {
     u32 orig;   /* encoder: the original pixel                                                */
 };
 
+/* Phase P of the feedback modes for pixel (i, j), i >= 1: neighbours of the two rows above with the
+ * reference's border fallbacks (R: NBLIC.c:288-303) and the a-free partial sums. */
+NB_DEV PixRec make_pixrec(const uint8_t *row, int w, int i, int j, u32 orig) {
+    PixRec pr;
+    pr.orig = orig;
+    const uint8_t *r1 = row - w, *r2 = r1 - w;
+    const bool up2 = i >= 2, l1 = j >= 1, l2 = j >= 2, rt1 = j + 1 < w, rt2 = j + 2 < w;
+    const int b = r1[j];
+    const int c = l1 ? (int)r1[j - 1] : b;
+    const int d = rt1 ? (int)r1[j + 1] : b;
+    const int f = up2 ? (int)r2[j] : b;
+    const int g = (up2 && rt1) ? (int)r2[j + 1] : f;
+    const int hh = (up2 && l1) ? (int)r2[j - 1] : f;
+    const int q = l2 ? (int)r1[j - 2] : c;
+    const int r = (up2 && rt2) ? (int)r2[j + 2] : g;
+    const int s = (up2 && l2) ? (int)r2[j - 2] : hh;
+    const int t = rt2 ? (int)r1[j + 2] : d;
+    pr.bcdf = (u32)b | ((u32)c << 8) | ((u32)d << 16) | ((u32)f << 24);
+    pr.ghqr = (u32)g | ((u32)hh << 8) | ((u32)q << 16) | ((u32)r << 24);
+    const int act = abs(b - c) + abs(b - d) + abs(b - f) + abs(d - g);
+    pr.st_act = (u32)s | ((u32)t << 8) | ((u32)act << 16);
+    const int K0 = abs(c - q) + abs(b - c) + abs(d - b);
+    const int K1 = abs(c - hh) + abs(b - f) + abs(d - g);
+    const int K2 = abs(c - s) + abs(b - hh) + abs(d - f);
+    const int K3 = abs(c - f) + abs(b - g) + abs(d - r);
+    const int K4 = abs(2 * c - q - s) + abs(2 * b - c - hh) + abs(2 * d - b - f);
+    const int K5 = abs(2 * c - s - hh) + abs(2 * b - hh - f) + abs(2 * d - f - g);
+    const int K6 = abs(2 * c - hh - f) + abs(2 * b - f - g) + abs(2 * d - g - r);
+    pr.k01 = (u32)K0 | ((u32)K1 << 16); pr.k23 = (u32)K2 | ((u32)K3 << 16); pr.k45 = (u32)K4 | ((u32)K5 << 16);
+    pr.k6_lin = (u32)K6 | ((u32)(9 * b + 2 * d - 2 * c - f + 1024) << 16);
+    return pr;
+}
+/* Finish the 7-direction predictor from a record (words ra, rb) once a and e are known.  nb must already
+ * hold a, b, c, d, e, q.  R: NBLIC.c:307-364 / QNBLIC.c:94-143 */
+NB_DEV Pred finish_predictor(const Nb &nb, const uint4 &ra, const uint4 &rb) {
+    const int a = nb.a, e = nb.e;
+    const int c0 = 2 * (abs(a - e) + (int)(ra.w & 0xffffu)), c1 = 2 * (abs(a - nb.c) + (int)(ra.w >> 16));
+    const int c2 = 2 * (abs(a - nb.q) + (int)(rb.x & 0xffffu)), c3 = 2 * (abs(a - nb.b) + (int)(rb.x >> 16));
+    const int c4 = abs(2 * a - e - nb.q) + (int)(rb.y & 0xffffu), c5 = abs(2 * a - nb.q - nb.c) + (int)(rb.y >> 16);
+    const int c6 = abs(2 * a - nb.c - nb.b) + (int)(rb.z & 0xffffu);
+    Pred pt;
+    int best = c0;
+    pt.ang2 = 2 * a;
+    if (c1 < best) { best = c1; pt.ang2 = 2 * nb.b; }
+    if (c2 < best) { best = c2; pt.ang2 = 2 * nb.c; }
+    if (c3 < best) { best = c3; pt.ang2 = 2 * nb.d; }
+    if (c4 < best) { best = c4; pt.ang2 = a + nb.c; }
+    if (c5 < best) { best = c5; pt.ang2 = nb.c + nb.b; }
+    if (c6 < best) { best = c6; pt.ang2 = nb.b + nb.d; }
+    pt.spread = c0 + c1 + c2 + c3 + c4 + c5 + c6 - 7 * best;
+    pt.lin16 = clampi(9 * a + (int)(rb.z >> 16) - 1024 - e, 0, 16 * 255);
+    return pt;
+}
+
 /* shared-memory image of one stream's adaptive state (one warp = one CTA).  The counter forest follows
  * as a separate, compacted array: class u only owns the (256 >> top) << (u / k_step) nodes its Golomb
  * order can reach (1000 nodes = 4 KB for lossless streams instead of 16 x 256). */
@@ -467,34 +521,9 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
             {
                 const int j = min(j0 + lane, w - 1);
                 PixRec pr;
-                pr.orig = DEC ? 0u : (u32)src[(size_t)i * w + j];
-                if (i >= 1) {
-                    const uint8_t *r1 = row - w, *r2 = r1 - w;
-                    const bool up2 = i >= 2, l1 = j >= 1, l2 = j >= 2, rt1 = j + 1 < w, rt2 = j + 2 < w;
-                    const int b = r1[j];
-                    const int c = l1 ? (int)r1[j - 1] : b;
-                    const int d = rt1 ? (int)r1[j + 1] : b;
-                    const int f = up2 ? (int)r2[j] : b;
-                    const int g = (up2 && rt1) ? (int)r2[j + 1] : f;
-                    const int hh = (up2 && l1) ? (int)r2[j - 1] : f;
-                    const int q = l2 ? (int)r1[j - 2] : c;
-                    const int r = (up2 && rt2) ? (int)r2[j + 2] : g;
-                    const int s = (up2 && l2) ? (int)r2[j - 2] : hh;
-                    const int t = rt2 ? (int)r1[j + 2] : d;
-                    pr.bcdf = (u32)b | ((u32)c << 8) | ((u32)d << 16) | ((u32)f << 24);
-                    pr.ghqr = (u32)g | ((u32)hh << 8) | ((u32)q << 16) | ((u32)r << 24);
-                    const int act = abs(b - c) + abs(b - d) + abs(b - f) + abs(d - g);
-                    pr.st_act = (u32)s | ((u32)t << 8) | ((u32)act << 16);
-                    const int K0 = abs(c - q) + abs(b - c) + abs(d - b);
-                    const int K1 = abs(c - hh) + abs(b - f) + abs(d - g);
-                    const int K2 = abs(c - s) + abs(b - hh) + abs(d - f);
-                    const int K3 = abs(c - f) + abs(b - g) + abs(d - r);
-                    const int K4 = abs(2 * c - q - s) + abs(2 * b - c - hh) + abs(2 * d - b - f);
-                    const int K5 = abs(2 * c - s - hh) + abs(2 * b - hh - f) + abs(2 * d - f - g);
-                    const int K6 = abs(2 * c - hh - f) + abs(2 * b - f - g) + abs(2 * d - g - r);
-                    pr.k01 = (u32)K0 | ((u32)K1 << 16); pr.k23 = (u32)K2 | ((u32)K3 << 16); pr.k45 = (u32)K4 | ((u32)K5 << 16);
-                    pr.k6_lin = (u32)K6 | ((u32)(9 * b + 2 * d - 2 * c - f + 1024) << 16);
-                } else { pr.bcdf = pr.ghqr = pr.st_act = pr.k01 = pr.k23 = pr.k45 = pr.k6_lin = 0; }
+                const u32 orig = DEC ? 0u : (u32)src[(size_t)i * w + j];
+                if (i >= 1) pr = make_pixrec(row, w, i, j, orig);
+                else { pr.bcdf = pr.ghqr = pr.st_act = pr.k01 = pr.k23 = pr.k45 = pr.k6_lin = 0; pr.orig = orig; }
                 smf.rec[lane] = pr;
                 __syncwarp();
             }
@@ -535,22 +564,7 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
                 }
                 if (!ok1) { /* the 7-direction gradient predictor */
                     if (i >= 1) {
-                        const int a = nb.a, e = nb.e;
-                        const int c0 = 2 * (abs(a - e) + (int)(ra.w & 0xffffu)), c1 = 2 * (abs(a - nb.c) + (int)(ra.w >> 16));
-                        const int c2 = 2 * (abs(a - nb.q) + (int)(rb.x & 0xffffu)), c3 = 2 * (abs(a - nb.b) + (int)(rb.x >> 16));
-                        const int c4 = abs(2 * a - e - nb.q) + (int)(rb.y & 0xffffu), c5 = abs(2 * a - nb.q - nb.c) + (int)(rb.y >> 16);
-                        const int c6 = abs(2 * a - nb.c - nb.b) + (int)(rb.z & 0xffffu);
-                        Pred pt;
-                        int best = c0;
-                        pt.ang2 = 2 * a;
-                        if (c1 < best) { best = c1; pt.ang2 = 2 * nb.b; }
-                        if (c2 < best) { best = c2; pt.ang2 = 2 * nb.c; }
-                        if (c3 < best) { best = c3; pt.ang2 = 2 * nb.d; }
-                        if (c4 < best) { best = c4; pt.ang2 = a + nb.c; }
-                        if (c5 < best) { best = c5; pt.ang2 = nb.c + nb.b; }
-                        if (c6 < best) { best = c6; pt.ang2 = nb.b + nb.d; }
-                        pt.spread = c0 + c1 + c2 + c3 + c4 + c5 + c6 - 7 * best;
-                        pt.lin16 = clampi(9 * a + (int)(rb.z >> 16) - 1024 - e, 0, 16 * 255);
+                        const Pred pt = finish_predictor(nb, ra, rb);
                         px0 = blend_prediction(pt, n_weight(pt.spread));
                     } else {
                         const Pred pt = predictor_terms(nb);

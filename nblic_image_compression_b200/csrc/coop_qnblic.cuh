@@ -1,0 +1,282 @@
+/*
+ * coop_qnblic.cuh -- warp-cooperative QNBLIC ("Q0.2", effort 0): one stream per warp.
+ *
+ * Encoder (R: QNBLIC.c:562-655).  Pass 1 is data parallel except for the bias table: lanes take 32
+ * consecutive pixels, compute the whole front end, then apply / train the bias entries in rounds --
+ * __match_any groups the lanes that hit the same table address, and round r lets the r-th member of
+ * every group through, so each address sees its pixels in raster order while different addresses
+ * proceed together.  Histogram counts are shared-memory atomics (order-free).  The 12 histograms are
+ * normalised, described and accumulated by 12 lanes side by side.  Pass 2, the reverse rANS sweep, is
+ * the only sequential chain: lanes prefetch 32 symbols' (freq, cumulative) and a 32-bit reciprocal of
+ * freq, the state update then costs one multiply-high, one multiply-back and a correction.
+ *
+ * Decoder (R: QNBLIC.c:493-555): per pixel sequential (the prediction needs the previous pixel), with
+ * the two rows above pre-reduced by 32 lanes (coop_nblic.cuh: make_pixrec) and the symbol found by two
+ * ballots over the cumulative table (32 coarse + 8 fine probes) instead of the reference's 384 KB LUT.
+ *
+ * Rows 0 and 1 keep QNBLIC's literal shift-register neighbourhood (R: QNBLIC.c:67-79), which differs
+ * from positional sampling there; from row 2 on the two agree except e at column 1 (= the old a).
+ */
+#pragma once
+#include "codec_core.cuh"
+#include "coop_nblic.cuh"
+
+namespace nblic {
+
+struct QCoopSmem {
+    int ctx[Q_CTX_ENTRIES]; /* 12 KB bias-cancel table                                           */
+    u32 tab[Q_TAB_ENTRIES]; /* 12 KB counts, then freq | cumulative << 16                        */
+    PixRec rec[32];         /*  1 KB decoder: phase-P records                                    */
+};
+
+/* rows 0 and 1 (and any row of a sequential fallback): the reference loop, warp-uniform, leader stores */
+template <bool DEC, class OnPixel>
+NB_DEV void q_serial_row(const uint8_t *img, int w, int i, QCoopSmem &sm, int lane, OnPixel on_pixel) {
+    Nb nb;
+    int err = 0;
+    sample_positional(img, w, i, 0, nb);
+    for (int j = 0; j < w; j++) {
+        const Pred pt = predictor_terms(nb);
+        const int px0 = blend_prediction(pt, q_weight(pt.spread));
+        const int cls = q_class(activity(nb, err));
+        const int adr = q_ctx_address(nb, px0, cls);
+        const int c = sm.ctx[adr];
+        int px, sign;
+        q_bias_apply(c, px0, px, sign);
+        const int x = on_pixel(j, cls, px, sign); /* encoder: reads x and records y; decoder: decodes x */
+        err = x - px0;
+        __syncwarp();
+        if (lane == 0) sm.ctx[adr] = q_bias_learn(c, err);
+        __syncwarp();
+        q_window_shift(img, w, i, j, x, nb);
+    }
+}
+
+/* writes the 12 histogram descriptions; lanes 0..11 work side by side.  Returns the advanced word index. */
+NB_DEV u32 q_finish_histograms(QCoopSmem &sm, uint16_t *out, u32 o, u32 cap, int lane) {
+    u32 mine = 0;
+    if (lane < Q_CLASSES) {
+        q_normalise(sm.tab + lane * 256);
+        mine = q_put_hist(out, 0, 0, sm.tab + lane * 256); /* dry run: cap 0 suppresses the stores */
+    }
+    u32 before = mine; /* exclusive prefix over lanes */
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) { const u32 t = __shfl_up_sync(FULL, before, d); if (lane >= d) before += t; }
+    before -= mine;
+    if (lane < Q_CLASSES) {
+        q_put_hist(out + o + before, 0, o + before < cap ? cap - (o + before) : 0, sm.tab + lane * 256);
+        q_pack_cumulative(sm.tab + lane * 256);
+    }
+    const u32 total = __shfl_sync(FULL, before + mine, Q_CLASSES - 1);
+    __syncwarp();
+    return o + total;
+}
+
+__device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u32 cap, uint8_t *sym8, QCoopSmem &sm, int lane, u32 &head_words,
+                              u32 &tail_words) {
+    uint16_t *sym = reinterpret_cast<uint16_t *>(sym8); /* cls | y << 8 per pixel, raster order */
+    for (int k = lane; k < Q_CTX_ENTRIES; k += 32) { sm.ctx[k] = 0; sm.tab[k] = 0; }
+    __syncwarp();
+
+    for (int i = 0; i < h; i++) { /* pass 1: model every pixel.  R: QNBLIC.c:586-623 */
+        const uint8_t *row = img + (size_t)i * w;
+        if (i < 2) {
+            q_serial_row<false>(img, w, i, sm, lane, [&](int j, int cls, int px, int sign) {
+                const int x = row[j];
+                const int y = q_fold(x, px, sign);
+                if (lane == 0) { sym[(size_t)i * w + j] = (uint16_t)(cls | (y << 8)); sm.tab[cls * 256 + y]++; }
+                return x;
+            });
+            continue;
+        }
+        int carry_px0 = 0;
+        for (int j0 = 0; j0 < w; j0 += 32) {
+            const bool active = j0 + lane < w;
+            const int j = min(j0 + lane, w - 1);
+            Nb nb;
+            sample_positional(img, w, i, j, nb);
+            if (j == 1) nb.e = row[-w]; /* the shift register still holds the old a = img[i-1][0] */
+            const Pred pt = predictor_terms(nb);
+            const int px0 = blend_prediction(pt, q_weight(pt.spread));
+            const int x = row[j];
+            int px0_left = __shfl_up_sync(FULL, px0, 1);
+            if (lane == 0) px0_left = carry_px0;
+            const int err_in = j == 0 ? 0 : (int)row[j - 1] - px0_left;
+            const int cls = q_class(activity(nb, err_in));
+            const int adr = active ? q_ctx_address(nb, px0, cls) : 0x10000 + lane;
+            carry_px0 = __shfl_sync(FULL, px0, 31);
+
+            /* bias table: same-address pixels in raster order, different addresses together */
+            const unsigned peers = __match_any_sync(FULL, adr);
+            const int my_turn = __popc(peers & ((1u << lane) - 1u));
+            const int rounds = __reduce_max_sync(FULL, active ? __popc(peers) : 0);
+            int y = 0;
+            for (int r = 0; r < rounds; r++) {
+                if (active && my_turn == r) {
+                    const int c = sm.ctx[adr];
+                    int px, sign;
+                    q_bias_apply(c, px0, px, sign);
+                    y = q_fold(x, px, sign);
+                    sm.ctx[adr] = q_bias_learn(c, x - px0);
+                }
+                __syncwarp();
+            }
+            if (active) {
+                atomicAdd(&sm.tab[cls * 256 + y], 1u);
+                sym[(size_t)i * w + j] = (uint16_t)(cls | (y << 8));
+            }
+        }
+    }
+    __syncwarp();
+
+    if (cap < 8) return false;
+    if (lane == 0) { out[0] = 0x3051; out[1] = 0x322e; out[2] = (uint16_t)h; out[3] = (uint16_t)w; } /* R: QNBLIC.c:463-473 */
+    const u32 o = q_finish_histograms(sm, out, 4, cap, lane);
+    if (o >= cap) return false;
+
+    /* pass 2: rANS, last pixel first, words written downwards from the end of the slot.  R: QNBLIC.c:238-253,635-650 */
+    u32 state = 1u << 16, p = cap;
+    bool ok = true;
+    const long long n = (long long)h * w;
+    for (long long base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
+        const long long idx = base + lane;
+        const bool valid = idx < n;
+        const u32 pair = valid ? (u32)sym[idx] : 0u;
+        const u32 e = sm.tab[(pair & 255u) * 256 + (pair >> 8)];
+        const u32 m = 0xffffffffu / max(e & 0xffffu, 1u); /* floor((2^32 - 1) / freq): quotient estimate low by at most 2 */
+        const int last = (int)min(31ll, n - 1 - base);
+        for (int jj = last; jj >= 0; jj--) {
+            const u32 ej = __shfl_sync(FULL, e, jj), mj = __shfl_sync(FULL, m, jj);
+            const u32 f = ej & 0xffffu, cum = ej >> 16;
+            u32 q = __umulhi(state, mj), r = state - q * f;
+            if (r >= f) { q++; r -= f; }
+            if (r >= f) { q++; r -= f; }
+            if (q > 0x1ffffu) {
+                if (p > o) { p--; if (lane == 0) out[p] = (uint16_t)state; } else ok = false;
+                state >>= 16;
+                q = __umulhi(state, mj); r = state - q * f;
+                if (r >= f) { q++; r -= f; }
+                if (r >= f) { q++; r -= f; }
+            }
+            state = r + (q << Q_NORM_BITS) + cum;
+        }
+    }
+    if (p >= o + 2) { p -= 2; if (lane == 0) { out[p + 1] = (uint16_t)state; out[p] = (uint16_t)(state >> 16); } } else ok = false;
+    head_words = o; tail_words = cap - p;
+    return ok;
+}
+
+/* 16-bit word reader over 128-byte lines (one 32-bit word per lane) */
+struct WordReader {
+    const uint16_t *base;
+    u32 len, pos, word;
+    unsigned long long line;
+    int lane;
+    NB_DEV void start(const uint16_t *p, u32 n_words, u32 at, int ln) { base = p; len = n_words; pos = at; word = 0; line = 0; lane = ln; }
+    NB_DEV u32 get() {
+        if (pos >= len) { pos++; return 0u; }
+        const unsigned long long a = (unsigned long long)(base + pos);
+        if ((a & ~127ull) != line) { line = a & ~127ull; word = *reinterpret_cast<const u32 *>(line + 4ull * (unsigned)lane); }
+        const u32 wsel = __shfl_sync(FULL, word, (int)((a >> 2) & 31ull));
+        pos++;
+        return (a & 2ull) ? (wsel >> 16) : (wsel & 0xffffu);
+    }
+};
+
+__device__ void coop_q_decode(const uint16_t *in, u32 avail, uint8_t *img, int h, int w, QCoopSmem &sm, int lane) {
+    for (int k = lane; k < Q_CTX_ENTRIES; k += 32) sm.ctx[k] = 0;
+    u32 rd = 4;
+    if (lane == 0) { /* the 12 histogram descriptions are one sequential code stream.  R: QNBLIC.c:415-459 */
+        for (int c = 0; c < Q_CLASSES; c++) {
+            u32 *hist = sm.tab + c * 256;
+            for (int k = 0; k < 256; k++) hist[k] = 0;
+            u32 pos = 0, sum = 0;
+#define Q_NEXT_() (rd < avail ? (u32)in[rd++] : (rd++, 0u))
+#define Q_PUSH_(val) do { const u32 v_ = (val); if (pos < 256) { hist[pos] = v_; sum += v_; } pos++; } while (0)
+            while (pos < 256 && sum < Q_NORM_SUM) {
+                const u32 code = Q_NEXT_();
+                if ((code >> 15) == 0) { Q_PUSH_(code); }
+                else if ((code >> 14) == 2) { Q_PUSH_((code >> 7) & 0x7f); Q_PUSH_(code & 0x7f); }
+                else if ((code >> 12) == 12) { Q_PUSH_((code >> 8) & 15); Q_PUSH_((code >> 4) & 15); Q_PUSH_(code & 15); }
+                else if ((code >> 12) == 13) { Q_PUSH_((code >> 9) & 7); Q_PUSH_((code >> 6) & 7); Q_PUSH_((code >> 3) & 7); Q_PUSH_(code & 7); }
+                else {
+                    u32 run = (code & 0xff) + 4;
+                    const u32 closer = (code >> 8) & 15, bit = (code >> 12) & 1;
+                    while (run--) Q_PUSH_(bit);
+                    if (closer != bit) Q_PUSH_(closer);
+                }
+            }
+#undef Q_PUSH_
+#undef Q_NEXT_
+        }
+    }
+    rd = __shfl_sync(FULL, rd, 0);
+    __syncwarp();
+    if (lane < Q_CLASSES) q_pack_cumulative(sm.tab + lane * 256);
+    __syncwarp();
+
+    WordReader words;
+    words.start(in, avail, rd, lane);
+    u32 state = words.get() << 16; state |= words.get(); /* R: QNBLIC.c:256-260 */
+
+    auto decode_symbol = [&](int cls) -> int { /* R: QNBLIC.c:262-274 with the LUT replaced by two ballots */
+        const u32 slot = state & (Q_NORM_SUM - 1);
+        const u32 *tab = sm.tab + cls * 256;
+        const unsigned coarse = __ballot_sync(FULL, (tab[8 * lane] >> 16) <= slot);
+        const int c8 = 8 * (__popc(coarse) - 1);
+        const unsigned fine = __ballot_sync(FULL, lane < 8 && (tab[c8 + (lane & 7)] >> 16) <= slot);
+        const int y = c8 + __popc(fine) - 1;
+        const u32 e = tab[y];
+        state = (state >> Q_NORM_BITS) * (e & 0xffffu) + slot - (e >> 16);
+        if (state < (1u << 16)) state = (state << 16) | words.get();
+        return y;
+    };
+
+    for (int i = 0; i < h; i++) { /* R: QNBLIC.c:520-552 */
+        uint8_t *row = img + (size_t)i * w;
+        if (i < 2) {
+            q_serial_row<true>(img, w, i, sm, lane, [&](int j, int cls, int px, int sign) {
+                const int x = q_unfold(decode_symbol(cls), px, sign);
+                if (lane == 0) row[j] = (uint8_t)x;
+                __syncwarp();
+                return x;
+            });
+            continue;
+        }
+        int err = 0, x1 = 0, x2 = 0;
+        for (int j0 = 0; j0 < w; j0 += 32) {
+            sm.rec[lane] = make_pixrec(row, w, i, min(j0 + lane, w - 1), 0u);
+            __syncwarp();
+            const int n_here = min(32, w - j0);
+            u32 my_x = 0;
+            for (int jj = 0; jj < n_here; jj++) {
+                const int j = j0 + jj;
+                const uint4 ra = *reinterpret_cast<const uint4 *>(&sm.rec[jj]);
+                const uint4 rb = *(reinterpret_cast<const uint4 *>(&sm.rec[jj]) + 1);
+                Nb nb;
+                nb.b = ra.x & 255; nb.c = (ra.x >> 8) & 255; nb.d = (ra.x >> 16) & 255; nb.f = ra.x >> 24;
+                nb.g = ra.y & 255; nb.q = (ra.y >> 16) & 255;
+                nb.a = j == 0 ? nb.b : x1;
+                nb.e = j >= 2 ? x2 : (j == 1 ? nb.c : nb.a); /* column 1: the shift register still holds img[i-1][0] */
+                const Pred pt = finish_predictor(nb, ra, rb);
+                const int px0 = blend_prediction(pt, q_weight(pt.spread));
+                const int act = abs(nb.a - nb.e) + abs(nb.a - nb.c) + (int)(ra.z >> 16) + 2 * abs(err);
+                const int cls = q_class(act);
+                const int adr = q_ctx_address(nb, px0, cls);
+                const int c = sm.ctx[adr];
+                int px, sign;
+                q_bias_apply(c, px0, px, sign);
+                const int x = q_unfold(decode_symbol(cls), px, sign);
+                if (lane == jj) my_x = (u32)x;
+                err = x - px0;
+                if (lane == 0) sm.ctx[adr] = q_bias_learn(c, err);
+                x2 = x1; x1 = x;
+                __syncwarp();
+            }
+            if (lane < n_here) row[j0 + lane] = (uint8_t)my_x;
+            __syncwarp();
+        }
+    }
+}
+
+} /* namespace nblic */

@@ -28,6 +28,7 @@
 #include "../../include/nblic_b200.h"
 #include "codec_core.cuh"
 #include "coop_nblic.cuh"
+#include "coop_qnblic.cuh"
 
 using namespace nblic;
 
@@ -181,6 +182,30 @@ __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *
                 if (len == 0xffffffffu) { t.status = NBLIC_B200_OVERFLOW; t.head_len = 0; }
                 else t.head_len = len;
                 t.tail_len = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+/* Warp-cooperative QNBLIC kernel (coop_qnblic.cuh): one warp per CTA, bias table and the 12 histograms in
+ * shared memory. */
+template <bool DEC>
+__global__ void __launch_bounds__(32) coop_q_kernel(Task *tasks, const int *order, int n_order, int *queue) {
+    __shared__ QCoopSmem sm;
+    const int lane = threadIdx.x;
+    for (;;) {
+        int pos = lane == 0 ? atomicAdd(queue, 1) : 0;
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (pos >= n_order) break;
+        Task &t = tasks[order[pos]];
+        if (DEC) coop_q_decode(reinterpret_cast<const uint16_t *>(t.slot), t.slot_cap / 2, t.rec, t.h, t.w, sm, lane);
+        else {
+            u32 head = 0, tail = 0;
+            const bool ok = coop_q_encode(t.src, t.h, t.w, reinterpret_cast<uint16_t *>(t.slot), t.slot_cap / 2, t.sym, sm, lane, head, tail);
+            if (lane == 0) {
+                if (ok) { t.head_len = head * 2; t.tail_len = tail * 2; }
+                else { t.status = NBLIC_B200_OVERFLOW; t.head_len = t.tail_len = 0; }
             }
         }
         __syncwarp();
@@ -401,6 +426,17 @@ int launch_coder(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queu
     return launch_coder_t<KIND, DEC, MAP_LANE>(c, n_order, d_order, d_queue, plan, avp_stride);
 }
 
+template <bool DEC>
+int launch_coop_q(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_q_kernel<DEC>, 32, 0));
+    const int grid = std::min(n_order, c->sm_count * std::max(per_sm, 1));
+    coop_q_kernel<DEC><<<grid, 32, 0, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <int NAVP, int MODE>
 int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w, int max_nodes) {
     const size_t fixed = MODE == 0 ? sizeof(CoopSmem) : (NAVP > 0 ? sizeof(CoopSmemAvp) : sizeof(CoopSmemFeedback));
@@ -470,7 +506,7 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
         int *d_q = (int *)c->queue.p + g;
         int rc = 0;
         switch (g) {
-            case G_Q: rc = launch_coder<KIND_Q, DEC>(c, cnt, d_ord, d_q, 1, 0); break;
+            case G_Q: rc = coop_ok ? launch_coop_q<DEC>(c, cnt, d_ord, d_q) : launch_coder<KIND_Q, DEC>(c, cnt, d_ord, d_q, 1, 0); break;
             case G_SEQ: rc = launch_coder<KIND_N, DEC>(c, cnt, d_ord, d_q, max_w[g], seq_effort); break;
             case G_E1_LOSSLESS: rc = launch_coop<0, 0>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
             case G_FB1: rc = launch_coop<0, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
@@ -478,7 +514,7 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
             case G_FB3: rc = launch_coop<10, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
         }
         if (rc) return -1;
-        if (g >= G_E1_LOSSLESS) c->last_map = "warp-coop";
+        if (g >= G_E1_LOSSLESS || (g == G_Q && coop_ok)) c->last_map = "warp-coop";
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     return 0;

@@ -236,6 +236,21 @@ def test_bad_and_ragged_inputs(api, codec):
     assert status == [api.OVERFLOW]
 
 
+def test_extreme_shapes_vs_oracle(api, codec, oracle):
+    """Maximum width / height (65535, NBLIC.h:29-30) and other degenerate aspect ratios."""
+    rng = np.random.default_rng(99)
+    shapes = [(1, 65535), (65535, 1), (3, 40000), (5000, 7), (2, 33), (33, 2)]
+    imgs = []
+    for h, w in shapes:
+        base = np.cumsum(rng.integers(-3, 4, size=h * w)).reshape(h, w) // 2 + 128
+        imgs.append(np.clip(base + rng.integers(-2, 3, size=(h, w)), 0, 255).astype(np.uint8))
+    for effort, near in [(0, 0), (1, 0), (1, 4)]:
+        _check_batch(api, codec, oracle, imgs, effort, near, api.MAP_AUTO)
+    small = [im[:, :3000] if im.shape[1] > 3000 else im[:3000] for im in imgs]
+    for effort, near in [(2, 0), (3, 2)]:
+        _check_batch(api, codec, oracle, small, effort, near, api.MAP_AUTO)
+
+
 def test_full_size_round_trip_properties(api, codec):
     """BASELINE.json sizes the oracle cannot finish quickly: encode -> decode identity, near bound."""
     import torch
