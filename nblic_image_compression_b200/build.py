@@ -13,9 +13,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnblic_b200.so")
+CLI = os.path.join(HERE, "nblic_batch")  # batch command-line front end (csrc/nblic_batch_cli.c)
 SOURCES_CU = ["stream_kernels.cu"]
 SOURCES_C = ["nblic_dropin.c"]
-HEADERS = [os.path.join(CSRC, "codec_core.cuh"), os.path.join(HERE, "..", "include", "nblic_b200.h")]
+HEADERS = [os.path.join(CSRC, h) for h in ("codec_core.cuh", "coop_nblic.cuh", "coop_avp.cuh", "coop_qnblic.cuh", "nblic_batch_cli.c")] + \
+          [os.path.join(HERE, "..", "include", "nblic_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=false"]
 
@@ -53,6 +55,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         subprocess.run(["gcc", "-O2", "-fPIC", "-Wall", "-Wextra", "-std=gnu99", "-c", os.path.join(CSRC, s), "-o", o], check=True)
         objs.append(o)
     subprocess.run([_nvcc(), "-shared", "-o", LIB, *objs, "-lpthread", "-cudart", "shared"], check=True)
+    subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-std=gnu99", "-o", CLI, os.path.join(CSRC, "nblic_batch_cli.c"),
+                    "-L" + HERE, "-lnblic_b200", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
 
 

@@ -101,19 +101,21 @@ NB_DEV Pred finish_predictor(const Nb &nb, const uint4 &ra, const uint4 &rb) {
  * order can reach (1000 nodes = 4 KB for lossless streams instead of 16 x 256). */
 struct CoopSmem {
     int16_t ctx[N_CTX_ENTRIES];        /*  4 KB: bias-cancel table                                    */
-    uint8_t rank[N_RANK_ENTRIES];      /* 10 KB: encoder: symbol -> rank; decoder: rank -> symbol       */
     uint16_t soft[208];                /* activity (clamped to 200) -> u | v << 4 | wv << 8             */
     uint16_t fbase[N_CLASSES];         /* first forest slot of class u                                 */
 };
-/* the feedback modes add the phase-P records of the current block */
-struct CoopSmemFeedback {
-    CoopSmem st;
-    PixRec rec[32];                    /*  1 KB                                                        */
-};
-/* efforts 2 / 3 add the two augmented systems of the least-squares predictor */
-struct CoopSmemAvp {
-    CoopSmemFeedback fb;
-    AvpSmem avp;
+/* Dynamic shared memory of a coop_nblic_kernel CTA, in this order:
+ *   CoopSmem | PixRec[32] (feedback modes) | AvpSmem (efforts 2/3) | rank[512*20] bytes (effort 1) | forest[]
+ * The rank tables (10 KB: encoder symbol -> rank, decoder rank -> symbol) stay in shared memory for
+ * effort 1; efforts 2/3 spend ~40k cycles per pixel in the least-squares solve, so there the tables move
+ * to global memory (L2) and the freed space buys 16 instead of 10 resident streams per SM. */
+template <int NAVP, int MODE> struct CoopLayout {
+    static constexpr bool kFeedback = MODE != 0;
+    static constexpr bool kRankGlobal = NAVP > 0;
+    static constexpr size_t kRecOff = (sizeof(CoopSmem) + 15) & ~(size_t)15;
+    static constexpr size_t kAvpOff = kRecOff + (kFeedback ? sizeof(PixRec) * 32 : 0);
+    static constexpr size_t kRankOff = kAvpOff + (NAVP > 0 ? sizeof(AvpSmem) : 0);
+    static constexpr size_t kForestOff = (kRankOff + (kRankGlobal ? 0 : N_RANK_ENTRIES) + 15) & ~(size_t)15;
 };
 
 /* number of forest nodes a stream with this k_step can touch (host and device) */
@@ -230,12 +232,12 @@ NB_DEV unsigned long long make_order_table(int k_step) {
 }
 NB_DEV int order_of(unsigned long long tab, int u) { return (int)((tab >> (4 * u)) & 15u); }
 
-NB_DEV void coop_reset(CoopSmem &sm, u32 *forest, int k_step, int *count, int lane) {
+NB_DEV void coop_reset(CoopSmem &sm, uint8_t *rank, u32 *forest, int k_step, int *count, int lane) {
     const int n_nodes = forest_nodes(k_step), top = (N_CLASSES - 1) / k_step;
     for (int k = lane; k < n_nodes; k += 32) forest[k] = (u32)N_MIX | ((u32)N_MIX << 16);
     if (lane < N_CLASSES) { int b = 0; for (int u = 0; u < lane; u++) b += (256 >> top) << (u / k_step); sm.fbase[lane] = (uint16_t)b; }
     for (int k = lane; k < N_CTX_ENTRIES; k += 32) sm.ctx[k] = 0;
-    for (int k = lane; k < N_RANK_ENTRIES; k += 32) { const int r = k % N_RANKS; sm.rank[k] = (uint8_t)r; count[k] = 2 * (N_RANKS - 1 - r); }
+    for (int k = lane; k < N_RANK_ENTRIES; k += 32) { const int r = k % N_RANKS; rank[k] = (uint8_t)r; count[k] = 2 * (N_RANKS - 1 - r); }
     for (int d = lane; d <= 200; d += 32) { int u, v, wv; n_soft_class(d, u, v, wv); sm.soft[d] = (uint16_t)(u | (v << 4) | (wv << 8)); }
     __syncwarp();
 }
@@ -382,8 +384,9 @@ NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, in
 /* ---- rank mapper, lane s holds entry s of the key's table ---------------------------------------- */
 /* Both directions first fetch the key's 20 table entries and frequencies (lane s < 20 holds entry s);
  * the frequencies live in global memory (L2), so the fetch is issued before the symbol is coded. */
-NB_DEV void coop_rank_fetch(const CoopSmem &sm, const int *count, int key, int lane, int &my_tab, int &my_count) {
-    my_tab = lane < N_RANKS ? (int)sm.rank[key + lane] : 255;
+template <bool RG>
+NB_DEV void coop_rank_fetch(const uint8_t *rank, const int *count, int key, int lane, int &my_tab, int &my_count) {
+    my_tab = lane < N_RANKS ? (int)(RG ? __ldcg(rank + key + lane) : rank[key + lane]) : 255;
     my_count = lane < N_RANKS ? __ldcg(count + key + lane) : 0;
 }
 /* encoder: table = symbol -> rank */
@@ -391,7 +394,7 @@ NB_DEV int coop_rank_encode(int y, int my_rank) {
     const int zr = __shfl_sync(FULL, my_rank, y & 31);
     return y < N_RANKS ? zr : y;
 }
-NB_DEV void coop_rank_touch_encode(CoopSmem &sm, int *count, int key, int y, int z, int lane, int my_rank, int my_count) {
+NB_DEV void coop_rank_touch_encode(uint8_t *rank, int *count, int key, int y, int z, int lane, int my_rank, int my_count) {
     if (y >= N_RANKS) return;
     const int cz = __shfl_sync(FULL, my_count, z) + 1;
     const int cp = __shfl_sync(FULL, my_count, max(z - 1, 0));
@@ -400,12 +403,12 @@ NB_DEV void coop_rank_touch_encode(CoopSmem &sm, int *count, int key, int y, int
         if (z > 0 && cp < cz) { /* one adjacent promotion (R: NBLIC.c:513-521) */
             const int other = __ffs(holders) - 1;
             count[key + z] = cp; count[key + z - 1] = cz;
-            sm.rank[key + y] = (uint8_t)(z - 1); sm.rank[key + other] = (uint8_t)z;
+            rank[key + y] = (uint8_t)(z - 1); rank[key + other] = (uint8_t)z;
         } else count[key + z] = cz;
     }
 }
 /* decoder: table = rank -> symbol.  Returns y and performs the update. */
-NB_DEV int coop_rank_decode(CoopSmem &sm, int *count, int key, int z, int lane, int my_sym, int my_count) {
+NB_DEV int coop_rank_decode(uint8_t *rank, int *count, int key, int z, int lane, int my_sym, int my_count) {
     if (z >= N_RANKS) return z;
     const int y = __shfl_sync(FULL, my_sym, z);
     const int other = __shfl_sync(FULL, my_sym, max(z - 1, 0));
@@ -414,7 +417,7 @@ NB_DEV int coop_rank_decode(CoopSmem &sm, int *count, int key, int z, int lane, 
     if (lane == 0) {
         if (z > 0 && cp < cz) {
             count[key + z] = cp; count[key + z - 1] = cz;
-            sm.rank[key + z] = (uint8_t)other; sm.rank[key + z - 1] = (uint8_t)y;
+            rank[key + z] = (uint8_t)other; rank[key + z - 1] = (uint8_t)y;
         } else count[key + z] = cz;
     }
     return y;
@@ -425,11 +428,11 @@ NB_DEV int coop_rank_decode(CoopSmem &sm, int *count, int key, int z, int lane, 
  * `count`: the stream's rank-mapper frequency table in global memory ([512][20] int, indexed by rank).
  * `stream` must be 128-byte aligned.  Returns the stream length or 0xffffffff on overflow.
  */
-__device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, u32 *forest, int *count,
-                                        int lane) {
+__device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, uint8_t *rank, u32 *forest,
+                                        int *count, int lane) {
     const int k_step = 3, top = (N_CLASSES - 1) / k_step; /* near = 0 (R: NBLIC.c:769) */
     const unsigned long long ktab = make_order_table(k_step);
-    coop_reset(sm, forest, k_step, count, lane);
+    coop_reset(sm, rank, forest, k_step, count, lane);
     CoopCoder<false> rc;
     rc.out.start(stream, cap, lane);
     coop_put_header(rc, h, w, 0, k_step, 1);
@@ -471,10 +474,10 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
 
                 const int key = ((px << 1) | sign) * N_RANKS;
                 int my_rank, my_count;
-                coop_rank_fetch(sm, count, key, lane, my_rank, my_count);
+                coop_rank_fetch<false>(rank, count, key, lane, my_rank, my_count);
                 const int z = coop_rank_encode(y, my_rank);
                 coop_encode_symbol(rc, sm, forest, k_step, top, ktab, u, v, wv, z, lane);
-                coop_rank_touch_encode(sm, count, key, y, z, lane, my_rank, my_count);
+                coop_rank_touch_encode(rank, count, key, y, z, lane, my_rank, my_count);
                 __syncwarp();
             }
         }
@@ -493,15 +496,16 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
  */
 template <int NAVP, bool DEC>
 __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *out_rec, int h, int w, int near, int k_step, uint8_t *stream,
-                             u32 cap, CoopSmemFeedback &smf, AvpSmem *avp_sm, u32 *forest, i64 *Brow, i64 *Frow, int *count, int lane) {
-    CoopSmem &sm = smf.st;
+                             u32 cap, CoopSmem &sm, PixRec *recs, AvpSmem *avp_sm, uint8_t *rank, u32 *forest, i64 *Brow, i64 *Frow, int *count,
+                             int lane) {
+    constexpr bool RG = NAVP > 0; /* rank tables in global memory */
     constexpr int AN = NAVP > 0 ? NAVP : 1;
     constexpr int AM = AvpGeom<AN>::M, ANS = AvpGeom<AN>::NS;
     const int top = (N_CLASSES - 1) / k_step;
     const unsigned long long ktab = make_order_table(k_step);
     const int qn = 2 * near + 1;
     const u32 qmagic = 65536u / (u32)qn + 1u; /* n / qn == (n * qmagic) >> 16 for 0 <= n < 3400 */
-    coop_reset(sm, forest, k_step, count, lane);
+    coop_reset(sm, rank, forest, k_step, count, lane);
     i64 E[ANS], ridge = 8;
     if constexpr (NAVP > 0) {
         for (size_t k = lane; k < (size_t)w * AM; k += 32) Brow[k] = 0;
@@ -524,7 +528,7 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
                 const u32 orig = DEC ? 0u : (u32)src[(size_t)i * w + j];
                 if (i >= 1) pr = make_pixrec(row, w, i, j, orig);
                 else { pr.bcdf = pr.ghqr = pr.st_act = pr.k01 = pr.k23 = pr.k45 = pr.k6_lin = 0; pr.orig = orig; }
-                smf.rec[lane] = pr;
+                recs[lane] = pr;
                 __syncwarp();
             }
 
@@ -533,8 +537,8 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
             u32 my_x = 0;
             for (int jj = 0; jj < n_here; jj++) {
                 const int j = j0 + jj;
-                const uint4 ra = *reinterpret_cast<const uint4 *>(&smf.rec[jj]);
-                const uint4 rb = *(reinterpret_cast<const uint4 *>(&smf.rec[jj]) + 1);
+                const uint4 ra = *reinterpret_cast<const uint4 *>(&recs[jj]);
+                const uint4 rb = *(reinterpret_cast<const uint4 *>(&recs[jj]) + 1);
                 Nb nb;
                 if (i >= 1) {
                     nb.b = ra.x & 255; nb.c = (ra.x >> 8) & 255; nb.d = (ra.x >> 16) & 255; nb.f = ra.x >> 24;
@@ -583,18 +587,18 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
                 const int room = (int)(((u32)(min(px, 255 - px) + near) * qmagic) >> 16);
 
                 int y, my_tab, my_count;
-                coop_rank_fetch(sm, count, key, lane, my_tab, my_count);
+                coop_rank_fetch<RG>(rank, count, key, lane, my_tab, my_count);
                 if constexpr (DEC) {
                     const int z = coop_decode_symbol(rc, sm, forest, k_step, top, ktab, u, v, wv, lane);
                     if (z < 0) return 1u;
-                    y = coop_rank_decode(sm, count, key, z, lane, my_tab, my_count);
+                    y = coop_rank_decode(rank, count, key, z, lane, my_tab, my_count);
                 } else {
                     const int xo = (int)rb.w;
                     const int mag = (int)(((u32)(abs(xo - px) + near) * qmagic) >> 16);
                     y = mag <= 0 ? 0 : (mag <= room ? 2 * mag - ((xo >= px) ^ sign) : mag + room);
                     const int z = coop_rank_encode(y, my_tab);
                     coop_encode_symbol(rc, sm, forest, k_step, top, ktab, u, v, wv, z, lane);
-                    coop_rank_touch_encode(sm, count, key, y, z, lane, my_tab, my_count);
+                    coop_rank_touch_encode(rank, count, key, y, z, lane, my_tab, my_count);
                 }
 
                 /* reconstruction (R: NBLIC.c:449-466) */

@@ -157,8 +157,16 @@ template <int NAVP, int MODE>
 __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *order, int n_order, int *queue, int *counts, i64 *avp,
                                                         size_t avp_half) {
     extern __shared__ __align__(16) uint8_t smem[];
+    using L = CoopLayout<NAVP, MODE>;
     const int lane = threadIdx.x;
-    int *my_counts = counts + (size_t)blockIdx.x * N_RANK_ENTRIES;
+    /* per-CTA global scratch: [512][20] int frequencies, then (efforts 2/3) the [512][20] byte rank tables */
+    uint8_t *my_scratch = reinterpret_cast<uint8_t *>(counts) + (size_t)blockIdx.x * (N_RANK_ENTRIES * 5);
+    int *my_counts = reinterpret_cast<int *>(my_scratch);
+    CoopSmem &sm = *reinterpret_cast<CoopSmem *>(smem);
+    PixRec *recs = reinterpret_cast<PixRec *>(smem + L::kRecOff);
+    AvpSmem *asm_ = NAVP > 0 ? reinterpret_cast<AvpSmem *>(smem + L::kAvpOff) : nullptr;
+    uint8_t *rank = L::kRankGlobal ? my_scratch + N_RANK_ENTRIES * 4 : smem + L::kRankOff;
+    u32 *forest = reinterpret_cast<u32 *>(smem + L::kForestOff); /* sized by the host for the largest k_step of the launch */
     i64 *my_b = NAVP > 0 ? avp + (size_t)blockIdx.x * 2 * avp_half : nullptr;
     for (;;) {
         int pos = lane == 0 ? atomicAdd(queue, 1) : 0;
@@ -166,15 +174,12 @@ __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *
         if (pos >= n_order) break;
         Task &t = tasks[order[pos]];
         u32 len;
-        constexpr size_t fixed = MODE == 0 ? sizeof(CoopSmem) : (NAVP > 0 ? sizeof(CoopSmemAvp) : sizeof(CoopSmemFeedback));
-        u32 *forest = reinterpret_cast<u32 *>(smem + ((fixed + 15) & ~(size_t)15)); /* sized by the host for the largest k_step of the launch */
-        if constexpr (MODE == 0) len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, *reinterpret_cast<CoopSmem *>(smem), forest, my_counts, lane);
+        if constexpr (MODE == 0) len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, sm, rank, forest, my_counts, lane);
         else {
-            AvpSmem *asm_ = NAVP > 0 ? &reinterpret_cast<CoopSmemAvp *>(smem)->avp : nullptr;
             const bool lossless_enc = MODE == 1 && t.near == 0; /* neighbours are the source pixels themselves */
             len = coop_feedback<NAVP, MODE == 2>(t.src, lossless_enc ? t.src : t.rec, lossless_enc ? nullptr : t.rec, t.h, t.w, t.near, t.k_step,
-                                                 t.slot, t.slot_cap, *reinterpret_cast<CoopSmemFeedback *>(smem), asm_, forest, my_b,
-                                                 my_b ? my_b + avp_half : nullptr, my_counts, lane);
+                                                 t.slot, t.slot_cap, sm, recs, asm_, rank, forest, my_b, my_b ? my_b + avp_half : nullptr, my_counts,
+                                                 lane);
         }
         if (lane == 0) {
             if (MODE == 2) { if (len != 0) t.status = NBLIC_B200_CORRUPT; }
@@ -439,8 +444,7 @@ int launch_coop_q(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_que
 
 template <int NAVP, int MODE>
 int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w, int max_nodes) {
-    const size_t fixed = MODE == 0 ? sizeof(CoopSmem) : (NAVP > 0 ? sizeof(CoopSmemAvp) : sizeof(CoopSmemFeedback));
-    const size_t smem = ((fixed + 15) & ~(size_t)15) + sizeof(u32) * (size_t)max_nodes; /* fixed tables + the compacted counter forest */
+    const size_t smem = CoopLayout<NAVP, MODE>::kForestOff + sizeof(u32) * (size_t)max_nodes; /* fixed tables + the compacted counter forest */
     auto kern = coop_nblic_kernel<NAVP, MODE>;
     int per_sm = 0;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -452,7 +456,7 @@ int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue
         grid = (int)std::min<size_t>((size_t)grid, std::max<size_t>(((size_t)32 << 30) / (2 * avp_half * sizeof(i64)), 1));
         CK(c->avp.reserve((size_t)grid * 2 * avp_half * sizeof(i64)));
     }
-    CK(c->coop_counts.reserve((size_t)grid * N_RANK_ENTRIES * sizeof(int)));
+    CK(c->coop_counts.reserve((size_t)grid * N_RANK_ENTRIES * 5)); /* frequencies (int) + rank tables (bytes) per CTA */
     kern<<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (int *)c->coop_counts.p, (i64 *)c->avp.p, avp_half);
     c->launches++;
     CK(cudaGetLastError());

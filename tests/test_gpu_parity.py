@@ -221,6 +221,55 @@ def test_dropin_cli_matches_reference_cli(tmp_path, kodak, manifest):
         assert da.read_bytes() == db.read_bytes(), switches
 
 
+def _write_bmp_gray(path, img):
+    """8-bit palettised gray BMP, bottom-up, rows padded to 4 bytes (the layout src/FileIO.c:170-245 reads)."""
+    import struct
+    h, w = img.shape
+    stride = (w + 3) & ~3
+    rows = np.zeros((h, stride), np.uint8)
+    rows[:, :w] = img[::-1]
+    pal = b"".join(bytes((k, k, k, 0)) for k in range(256))
+    off = 14 + 40 + 1024
+    hdr = b"BM" + struct.pack("<IHHI", off + stride * h, 0, 0, off) + struct.pack("<IiiHHIIiiII", 40, w, h, 1, 8, 0, stride * h, 2835, 2835, 256, 0)
+    open(path, "wb").write(hdr + pal + rows.tobytes())
+
+
+def test_batch_cli_matches_reference_cli(tmp_path, kodak):
+    """csrc/nblic_batch_cli.c (the batch front end): PGM and BMP inputs, one batch call,
+    same .nblic bytes as the reference CLI run file by file; decode back to identical PGMs."""
+    import subprocess
+    from conftest import ROOT
+    cli = os.path.join(ROOT, "nblic_image_compression_b200", "nblic_batch")
+    theirs = os.path.join(ROOT, "oracle", "_ref", "nblic_codec_ref")
+    if not (os.path.exists(cli) and os.path.exists(theirs)):
+        pytest.skip("nblic_batch or the reference CLI not built")
+    inputs = []
+    for k, name in enumerate(("01", "04", "23")):
+        img = kodak[name][: 200 + 31 * k, : 301 + 7 * k]
+        path = tmp_path / (f"img{k}.bmp" if k == 1 else f"img{k}.pgm")
+        if k == 1:
+            _write_bmp_gray(path, img)
+        else:
+            path.write_bytes(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]) + img.tobytes())
+        inputs.append(path)
+    for switches in ("-cn0e0", "-cn0e1", "-cn3e1", "-cn1e3"):
+        out = tmp_path / ("o" + switches[1:]); out.mkdir()
+        subprocess.run([cli, switches, str(out), *map(str, inputs)], check=True, stdout=subprocess.DEVNULL)
+        streams = []
+        for path in inputs:
+            ref_out = tmp_path / "ref.nblic"
+            subprocess.run([theirs, switches, str(path), str(ref_out)], check=True, stdout=subprocess.DEVNULL)
+            mine = out / (path.stem + ".nblic")
+            assert mine.read_bytes() == ref_out.read_bytes(), (switches, path.name)
+            streams.append(mine)
+        dec = tmp_path / ("d" + switches[1:]); dec.mkdir()
+        subprocess.run([cli, "-d", str(dec), *map(str, streams)], check=True, stdout=subprocess.DEVNULL)
+        for path in streams:
+            ref_pgm = tmp_path / "ref.pgm"
+            subprocess.run([theirs, "-d", str(path), str(ref_pgm)], check=True, stdout=subprocess.DEVNULL)
+            assert (dec / (path.stem + ".pgm")).read_bytes() == ref_pgm.read_bytes(), (switches, path.name)
+
+
 def test_bad_and_ragged_inputs(api, codec):
     good = codec.encode_batch([gen(8, 8, 1)], 0, 1)[0][0]
     hdr = bytearray(good); hdr[15] = 4
