@@ -107,11 +107,12 @@ struct CoopSmem {
 /* Dynamic shared memory of a coop_nblic_kernel CTA, in this order:
  *   CoopSmem | PixRec[32] (feedback modes) | AvpSmem (efforts 2/3) | rank[512*20] bytes (effort 1) | forest[]
  * The rank tables (10 KB: encoder symbol -> rank, decoder rank -> symbol) stay in shared memory for
- * effort 1; efforts 2/3 spend ~40k cycles per pixel in the least-squares solve, so there the tables move
- * to global memory (L2) and the freed space buys 16 instead of 10 resident streams per SM. */
-template <int NAVP, int MODE> struct CoopLayout {
+ * effort 1 while the batch fits the 11 streams/SM that allows; efforts 2/3 spend ~40k cycles per pixel in
+ * the least-squares solve, so there (and for effort-1 batches larger than 11 x SMs images, RG = true) the
+ * tables move to global memory (L2) and the freed space buys 16 (efforts 2/3) or 24 resident streams. */
+template <int NAVP, int MODE, bool RG> struct CoopLayout {
     static constexpr bool kFeedback = MODE != 0;
-    static constexpr bool kRankGlobal = NAVP > 0;
+    static constexpr bool kRankGlobal = RG;
     static constexpr size_t kRecOff = (sizeof(CoopSmem) + 15) & ~(size_t)15;
     static constexpr size_t kAvpOff = kRecOff + (kFeedback ? sizeof(PixRec) * 32 : 0);
     static constexpr size_t kRankOff = kAvpOff + (NAVP > 0 ? sizeof(AvpSmem) : 0);
@@ -428,6 +429,7 @@ NB_DEV int coop_rank_decode(uint8_t *rank, int *count, int key, int z, int lane,
  * `count`: the stream's rank-mapper frequency table in global memory ([512][20] int, indexed by rank).
  * `stream` must be 128-byte aligned.  Returns the stream length or 0xffffffff on overflow.
  */
+template <bool RG>
 __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, uint8_t *rank, u32 *forest,
                                         int *count, int lane) {
     const int k_step = 3, top = (N_CLASSES - 1) / k_step; /* near = 0 (R: NBLIC.c:769) */
@@ -474,7 +476,7 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
 
                 const int key = ((px << 1) | sign) * N_RANKS;
                 int my_rank, my_count;
-                coop_rank_fetch<false>(rank, count, key, lane, my_rank, my_count);
+                coop_rank_fetch<RG>(rank, count, key, lane, my_rank, my_count);
                 const int z = coop_rank_encode(y, my_rank);
                 coop_encode_symbol(rc, sm, forest, k_step, top, ktab, u, v, wv, z, lane);
                 coop_rank_touch_encode(rank, count, key, y, z, lane, my_rank, my_count);
@@ -494,11 +496,10 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
  * Encoder: `stream` 128-byte aligned, cap = capacity; returns length or 0xffffffff.
  * Decoder: cap = valid bytes; returns 0, or 1 for a corrupt stream.
  */
-template <int NAVP, bool DEC>
+template <int NAVP, bool DEC, bool RG>
 __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *out_rec, int h, int w, int near, int k_step, uint8_t *stream,
                              u32 cap, CoopSmem &sm, PixRec *recs, AvpSmem *avp_sm, uint8_t *rank, u32 *forest, i64 *Brow, i64 *Frow, int *count,
                              int lane) {
-    constexpr bool RG = NAVP > 0; /* rank tables in global memory */
     constexpr int AN = NAVP > 0 ? NAVP : 1;
     constexpr int AM = AvpGeom<AN>::M, ANS = AvpGeom<AN>::NS;
     const int top = (N_CLASSES - 1) / k_step;

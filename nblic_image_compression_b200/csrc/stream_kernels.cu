@@ -153,11 +153,11 @@ __global__ void __launch_bounds__(32) coder_kernel(Task *tasks, const int *order
  * accumulators in `avp` (efforts 2 / 3: 2 * avp_half int64 per CTA).
  * MODE 0: lossless effort-1 encode (phase P = whole front end); 1: encode with a per-pixel front end
  * (near-lossless, and every effort-2/3 encode); 2: decode.  NAVP = 0 / 6 / 10 for effort 1 / 2 / 3. */
-template <int NAVP, int MODE>
+template <int NAVP, int MODE, bool RG>
 __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *order, int n_order, int *queue, int *counts, i64 *avp,
                                                         size_t avp_half) {
     extern __shared__ __align__(16) uint8_t smem[];
-    using L = CoopLayout<NAVP, MODE>;
+    using L = CoopLayout<NAVP, MODE, RG>;
     const int lane = threadIdx.x;
     /* per-CTA global scratch: [512][20] int frequencies, then (efforts 2/3) the [512][20] byte rank tables */
     uint8_t *my_scratch = reinterpret_cast<uint8_t *>(counts) + (size_t)blockIdx.x * (N_RANK_ENTRIES * 5);
@@ -174,10 +174,10 @@ __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *
         if (pos >= n_order) break;
         Task &t = tasks[order[pos]];
         u32 len;
-        if constexpr (MODE == 0) len = coop_e1_encode_lossless(t.src, t.h, t.w, t.slot, t.slot_cap, sm, rank, forest, my_counts, lane);
+        if constexpr (MODE == 0) len = coop_e1_encode_lossless<RG>(t.src, t.h, t.w, t.slot, t.slot_cap, sm, rank, forest, my_counts, lane);
         else {
             const bool lossless_enc = MODE == 1 && t.near == 0; /* neighbours are the source pixels themselves */
-            len = coop_feedback<NAVP, MODE == 2>(t.src, lossless_enc ? t.src : t.rec, lossless_enc ? nullptr : t.rec, t.h, t.w, t.near, t.k_step,
+            len = coop_feedback<NAVP, MODE == 2, RG>(t.src, lossless_enc ? t.src : t.rec, lossless_enc ? nullptr : t.rec, t.h, t.w, t.near, t.k_step,
                                                  t.slot, t.slot_cap, sm, recs, asm_, rank, forest, my_b, my_b ? my_b + avp_half : nullptr, my_counts,
                                                  lane);
         }
@@ -362,6 +362,7 @@ struct nblic_b200_ctx {
     uint64_t launches = 0;
     float coder_ms = 0.f;
     const char *last_map = "none";
+    int last_slots = 0; /* resident streams the most recent cooperative launch could hold */
     DevBuf tasks, order, queue, slots, sym, cold, coop_counts, avp, offsets, flags, pixels, streams, recon, peeks;
     int occ_warp[2] = {0, 0};
 };
@@ -442,14 +443,17 @@ int launch_coop_q(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_que
     return 0;
 }
 
-template <int NAVP, int MODE>
-int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w, int max_nodes) {
-    const size_t smem = CoopLayout<NAVP, MODE>::kForestOff + sizeof(u32) * (size_t)max_nodes; /* fixed tables + the compacted counter forest */
-    auto kern = coop_nblic_kernel<NAVP, MODE>;
+template <int NAVP, int MODE, bool RG>
+int launch_coop_t(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w, int max_nodes, bool probe_only, int *slots_out) {
+    const size_t smem = CoopLayout<NAVP, MODE, RG>::kForestOff + sizeof(u32) * (size_t)max_nodes; /* fixed tables + the compacted counter forest */
+    auto kern = coop_nblic_kernel<NAVP, MODE, RG>;
     int per_sm = 0;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
-    int grid = std::min(n_order, c->sm_count * std::max(per_sm, 1));
+    const int slots = c->sm_count * std::max(per_sm, 1);
+    if (slots_out) *slots_out = slots;
+    if (probe_only) return 0;
+    int grid = std::min(n_order, slots);
     size_t avp_half = 0;
     if (NAVP > 0) { /* B and F: one m-vector per image column each; bound the grid by a 32 GB budget */
         avp_half = (size_t)max_w * (1 + NAVP + NAVP * NAVP);
@@ -459,8 +463,23 @@ int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue
     CK(c->coop_counts.reserve((size_t)grid * N_RANK_ENTRIES * 5)); /* frequencies (int) + rank tables (bytes) per CTA */
     kern<<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (int *)c->coop_counts.p, (i64 *)c->avp.p, avp_half);
     c->launches++;
+    c->last_slots = slots;
     CK(cudaGetLastError());
     return 0;
+}
+
+/* Efforts 2/3 always keep the rank tables in L2.  Effort 1 keeps them in shared memory (lowest latency per
+ * pixel) unless the batch has more images than that layout can hold resident; then the L2 layout more than
+ * doubles the resident streams. */
+template <int NAVP, int MODE>
+int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w, int max_nodes) {
+    if (NAVP > 0) return launch_coop_t<NAVP, MODE, true>(c, n_order, d_order, d_queue, max_w, max_nodes, false, nullptr);
+    int slots_smem = 0;
+    if (launch_coop_t<NAVP, MODE, false>(c, n_order, d_order, d_queue, max_w, max_nodes, true, &slots_smem)) return -1;
+    const char *force = getenv("NBLIC_B200_RANK");  /* "smem" / "l2": override for experiments */
+    const bool use_l2 = force ? force[0] == 'l' : n_order > slots_smem;
+    if (use_l2) return launch_coop_t<NAVP, MODE, true>(c, n_order, d_order, d_queue, max_w, max_nodes, false, nullptr);
+    return launch_coop_t<NAVP, MODE, false>(c, n_order, d_order, d_queue, max_w, max_nodes, false, nullptr);
 }
 
 /* Upload tasks, run the coder kernels for the Q and N groups, download the task results. */
