@@ -148,9 +148,11 @@ NB_DEV void nstate_reset(const NState &s, int lane, int nl) {
     }
 }
 
-NB_DEV int n_weight(int spread) { /* R: NBLIC.c:308,365-367 */
-    return (spread >= 31) + (spread >= 93) + (spread >= 279) + (spread >= 620) + (spread >= 1550) + (spread >= 3410) +
-           (spread >= 9300) + (spread >= 24800);
+NB_DEV int n_weight(int spread) { /* R: NBLIC.c:308,365-367: number of thresholds {31,93,279,620,1550,3410,9300,24800} <= spread */
+    int w = spread >= 620 ? 4 : 0;                       /* three-level search instead of eight compares */
+    w += spread >= (w ? 3410 : 93) ? 2 : 0;
+    w += spread >= (w == 0 ? 31 : w == 2 ? 279 : w == 4 ? 1550 : 9300);
+    return w + (spread >= 24800);
 }
 
 /* Soft 16-class activity quantiser.  R: NBLIC.c:373-395 */

@@ -201,37 +201,38 @@ template <> struct CoopCoder<true> {
     }
 };
 
-NB_DEV u32 learn_packed(u32 c, int bit, int weight) { /* node_learn on the packed pair */
+/* node_learn on the packed pair n0 | n1 << 16 whose sum s = n0 + n1 the caller already knows (R: NBLIC.c:606-617) */
+NB_DEV u32 learn_packed(u32 c, u32 s, int bit, int weight) {
     c += (u32)weight << (bit ? 16 : 0);
-    if ((c & 0xffffu) + (c >> 16) > (u32)(N_MIX * 256)) c = ((c + 0x00010001u) >> 1) & 0x7fff7fffu;
+    if (s + (u32)weight > (u32)(N_MIX * 256)) c = ((c + 0x00010001u) >> 1) & 0x7fff7fffu;
     return c;
 }
-/* floor(4096 * n1 / (n0 + n1)) without the integer divide: float estimate (error < 2e-3), multiply back,
- * correct by one.  n0 + n1 <= 8224 and 4096 * n1 < 2^26 with 12 trailing zero bits, so both convert exactly. */
-NB_DEV int node_p1_fast(u32 packed) {
-    const u32 n1 = packed >> 16, s = (packed & 0xffffu) + n1, a = n1 << 12;
-    u32 q = __float2uint_rz(__fdividef(__uint2float_rn(a), __uint2float_rn(s)));
+NB_DEV u32 pair_sum(u32 c) { return (c & 0xffffu) + (c >> 16); }
+/* floor(4096 * n1 / s) without the integer divide: float estimate (error < 2e-3), multiply back,
+ * correct by one.  s <= 8224 and 4096 * n1 < 2^26 with 12 trailing zero bits, so both convert exactly. */
+NB_DEV int node_p1_fast(u32 packed, u32 s) {
+    const u32 a = (packed >> 16) << 12;
+    float rcp;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(__uint2float_rn(s)));
+    u32 q = __float2uint_rz(__uint2float_rn(a) * rcp);
     const int r = (int)a - (int)(q * s);
     if (r < 0) q--; else if (r >= (int)s) q++;
     return (int)q;
 }
-NB_DEV u32 mixed_p(u32 cu, u32 cv, int wv) { /* R: NBLIC.c:627-631 */
-    const int p = (node_p1_fast(cu) * (N_MIX - wv) + node_p1_fast(cv) * wv + N_MIX / 2) >> 5; /* operands >= 0: >> 5 == / 32 */
-    return (u32)clampi(p, 1, N_PROB_ONE - 1);
+/* R: NBLIC.c:627-631.  Both p1 are <= 4095 (n0 >= 1), so only the lower clip can act. */
+NB_DEV u32 mixed_p(u32 cu, u32 cv, u32 su, u32 sv, int wv) {
+    const int p = (node_p1_fast(cu, su) * (N_MIX - wv) + node_p1_fast(cv, sv) * wv + N_MIX / 2) >> 5; /* operands >= 0: >> 5 == / 32 */
+    return (u32)max(p, 1);
 }
 /* iu / iv: forest slots of the node in the main and the side class (equal when both are the same class) */
-NB_DEV void learn_pair(u32 *forest, int iu, int iv, u32 cu, u32 cv, int wv, int bit) {
-    if (iu == iv) forest[iu] = learn_packed(learn_packed(cu, bit, N_MIX - wv), bit, wv);
-    else { forest[iu] = learn_packed(cu, bit, N_MIX - wv); forest[iv] = learn_packed(cv, bit, wv); }
+NB_DEV void learn_pair(u32 *forest, int iu, int iv, u32 cu, u32 cv, u32 su, u32 sv, int wv, int bit) {
+    if (iu == iv) { const u32 c1 = learn_packed(cu, su, bit, N_MIX - wv); forest[iu] = learn_packed(c1, pair_sum(c1), bit, wv); }
+    else { forest[iu] = learn_packed(cu, su, bit, N_MIX - wv); forest[iv] = learn_packed(cv, sv, bit, wv); }
 }
 
-/* k = u / k_step for u = 0..15, 4 bits each */
-NB_DEV unsigned long long make_order_table(int k_step) {
-    unsigned long long t = 0;
-    for (int u = 0; u < N_CLASSES; u++) t |= (unsigned long long)(u / k_step) << (4 * u);
-    return t;
-}
-NB_DEV int order_of(unsigned long long tab, int u) { return (int)((tab >> (4 * u)) & 15u); }
+/* k = u / k_step for u = 0..15 as a multiply-shift: (u * (65536 / k_step + 1)) >> 16 is exact for 3 <= k_step <= 16 */
+NB_DEV u32 make_order_table(int k_step) { return 65536u / (u32)k_step + 1u; }
+NB_DEV int order_of(u32 magic, int u) { return (int)(((u32)u * magic) >> 16); }
 
 NB_DEV void coop_reset(CoopSmem &sm, uint8_t *rank, u32 *forest, int k_step, int *count, int lane) {
     const int n_nodes = forest_nodes(k_step), top = (N_CLASSES - 1) / k_step;
@@ -251,7 +252,7 @@ NB_DEV void coop_put_header(CoopCoder<false> &rc, int h, int w, int near, int k_
 }
 
 /* ---- encoder side of one symbol: every decision of the pixel in its own lane ------------------- */
-NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, u32 *forest, int k_step, int top, unsigned long long ktab, int u, int v, int wv,
+NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, u32 *forest, int k_step, int top, u32 ktab, int u, int v, int wv,
                                int z, int lane) {
     const int k = order_of(ktab, u);
     if (order_of(ktab, v) != k) v = u;
@@ -269,9 +270,9 @@ NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, u32 *forest, 
         }
         u32 coded = 0;
         if (lane < D) {
-            const u32 cu = forest[bu + slot], cv = forest[bv + slot];
-            coded = mixed_p(cu, cv, wv) | ((u32)bit << 12);
-            learn_pair(forest, bu + slot, bv + slot, cu, cv, wv, bit);
+            const u32 cu = forest[bu + slot], cv = forest[bv + slot], su = pair_sum(cu), sv = pair_sum(cv);
+            coded = mixed_p(cu, cv, su, sv, wv) | ((u32)bit << 12);
+            learn_pair(forest, bu + slot, bv + slot, cu, cv, su, sv, wv, bit);
         }
         for (int d = 0; d < D; d++) {
             const u32 cd = __shfl_sync(FULL, coded, d);
@@ -285,10 +286,10 @@ NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, u32 *forest, 
             if (phase == 0) bit = (node >> top) < (z >> kk);
             else bit = (z >> kk) & 1;
             const int slot = compact_node(node, top, k_tree);
-            const u32 cu = forest[iu_base + slot], cv = forest[iv_base + slot];
-            rc.bit(bit, mixed_p(cu, cv, wv));
+            const u32 cu = forest[iu_base + slot], cv = forest[iv_base + slot], su = pair_sum(cu), sv = pair_sum(cv);
+            rc.bit(bit, mixed_p(cu, cv, su, sv, wv));
             __syncwarp();
-            if (lane == 0) learn_pair(forest, iu_base + slot, iv_base + slot, cu, cv, wv, bit);
+            if (lane == 0) learn_pair(forest, iu_base + slot, iv_base + slot, cu, cv, su, sv, wv, bit);
             __syncwarp();
             if (phase == 0) {
                 if (!bit) { node++; kk--; phase = kk >= 0 ? 1 : 2; }
@@ -312,7 +313,7 @@ NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, u32 *forest, 
 
 /* ---- decoder side of one symbol ----------------------------------------------------------------- */
 /* Returns z, or -1 for a corrupt stream. */
-NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, int k_step, int top, unsigned long long ktab, int u, int v, int wv,
+NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, int k_step, int top, u32 ktab, int u, int v, int wv,
                               int lane) {
     int k = order_of(ktab, u);
     if (order_of(ktab, v) != k) v = u;
@@ -322,8 +323,8 @@ NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, in
     for (int base = 0; base < n_unary && q < 0; base += 32) {
         /* every lane evaluates one candidate node of the unary run */
         const int d = base + lane, slot = d << k;
-        u32 cu = 0, cv = 0, p = 0;
-        if (d < n_unary) { cu = forest[bu + slot]; cv = forest[bv + slot]; p = mixed_p(cu, cv, wv); }
+        u32 cu = 0, cv = 0, su = 64, sv = 64, p = 0;
+        if (d < n_unary) { cu = forest[bu + slot]; cv = forest[bv + slot]; su = pair_sum(cu); sv = pair_sum(cv); p = mixed_p(cu, cv, su, sv, wv); }
         const int lim = min(32, n_unary - base);
         int stop = -1;
         for (int dd = 0; dd < lim; dd++) {
@@ -331,7 +332,7 @@ NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, in
             if (!rc.bit(0, pd)) { stop = dd; break; }
         }
         const int last = stop >= 0 ? stop : lim - 1;
-        if (lane <= last) learn_pair(forest, bu + slot, bv + slot, cu, cv, wv, !(stop >= 0 && lane == stop));
+        if (lane <= last) learn_pair(forest, bu + slot, bv + slot, cu, cv, su, sv, wv, !(stop >= 0 && lane == stop));
         if (stop >= 0) q = base + stop;
     }
     __syncwarp();
@@ -341,10 +342,10 @@ NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, in
             if (uu >= N_CLASSES) return -1;
             k = order_of(ktab, uu);
             const int at = sm.fbase[uu] + compact_node(node, top, k);
-            const u32 c = forest[at];
-            const int bit = rc.bit(0, mixed_p(c, c, wv));
+            const u32 c = forest[at], sc = pair_sum(c);
+            const int bit = rc.bit(0, mixed_p(c, c, sc, sc, wv));
             __syncwarp();
-            if (lane == 0) learn_pair(forest, at, at, c, c, wv, bit);
+            if (lane == 0) learn_pair(forest, at, at, c, c, sc, sc, wv, bit);
             __syncwarp();
             if (!bit) break;
             node += 1 << top;
@@ -354,10 +355,10 @@ NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, in
         const int k_tree = k;
         for (node++, k--; k >= 0; k--) {
             const int at = sm.fbase[uu] + compact_node(node & 255, top, k_tree);
-            const u32 c = forest[at];
-            const int bit = rc.bit(0, mixed_p(c, c, wv));
+            const u32 c = forest[at], sc = pair_sum(c);
+            const int bit = rc.bit(0, mixed_p(c, c, sc, sc, wv));
             __syncwarp();
-            if (lane == 0) learn_pair(forest, at, at, c, c, wv, bit);
+            if (lane == 0) learn_pair(forest, at, at, c, c, sc, sc, wv, bit);
             __syncwarp();
             if (bit) z += 1 << k;
             node += bit ? (1 << k) : 1;
@@ -369,15 +370,15 @@ NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, in
         const int L = max(lane, 1), t = 31 - __clz(L), prefix = L ^ (1 << t);
         const bool valid = lane >= 1 && lane < (1 << k);
         const int slot = (q << k) + ((1 + (prefix << max(k - t, 0)) + t - __popc(prefix)) & ((1 << k) - 1));
-        u32 cu = 0, cv = 0, p = 0;
-        if (valid) { cu = forest[bu + slot]; cv = forest[bv + slot]; p = mixed_p(cu, cv, wv); }
+        u32 cu = 0, cv = 0, su = 64, sv = 64, p = 0;
+        if (valid) { cu = forest[bu + slot]; cv = forest[bv + slot]; su = pair_sum(cu); sv = pair_sum(cv); p = mixed_p(cu, cv, su, sv, wv); }
         int cur = 1;
         for (int s = 0; s < k; s++) {
             const u32 pd = __shfl_sync(FULL, p, cur);
             cur = 2 * cur + rc.bit(0, pd);
         }
         z += cur - (1 << k);
-        if (valid && (cur >> (k - t)) == lane) learn_pair(forest, bu + slot, bv + slot, cu, cv, wv, (cur >> (k - t - 1)) & 1);
+        if (valid && (cur >> (k - t)) == lane) learn_pair(forest, bu + slot, bv + slot, cu, cv, su, sv, wv, (cur >> (k - t - 1)) & 1);
     }
     return z;
 }
@@ -433,7 +434,7 @@ template <bool RG>
 __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, uint8_t *rank, u32 *forest,
                                         int *count, int lane) {
     const int k_step = 3, top = (N_CLASSES - 1) / k_step; /* near = 0 (R: NBLIC.c:769) */
-    const unsigned long long ktab = make_order_table(k_step);
+    const u32 ktab = make_order_table(k_step);
     coop_reset(sm, rank, forest, k_step, count, lane);
     CoopCoder<false> rc;
     rc.out.start(stream, cap, lane);
@@ -503,7 +504,7 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
     constexpr int AN = NAVP > 0 ? NAVP : 1;
     constexpr int AM = AvpGeom<AN>::M, ANS = AvpGeom<AN>::NS;
     const int top = (N_CLASSES - 1) / k_step;
-    const unsigned long long ktab = make_order_table(k_step);
+    const u32 ktab = make_order_table(k_step);
     const int qn = 2 * near + 1;
     const u32 qmagic = 65536u / (u32)qn + 1u; /* n / qn == (n * qmagic) >> 16 for 0 <= n < 3400 */
     coop_reset(sm, rank, forest, k_step, count, lane);
