@@ -445,6 +445,7 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
         int carry_px0 = 0; /* px0 of the pixel left of this block */
         for (int j0 = 0; j0 < w; j0 += 32) {
             /* ---------------- phase P: lane = pixel j0 + lane ---------------- */
+            const bool active = j0 + lane < w;
             const int j = min(j0 + lane, w - 1);
             Nb nb;
             sample_positional(img, w, i, j, nb);
@@ -455,32 +456,68 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
             if (lane == 0) px0_left = carry_px0;
             const int err_in = j == 0 ? 0 : clampi(nb.a - px0_left, -127, 127); /* nb.a is the coded value of pixel j-1 */
             const u32 soft = sm.soft[min(activity(nb, err_in), 200)];
-            const u32 adr = (((soft & 15u) >> 1) << 8) | (u32)texture_bits(nb, px0);
-            const u32 rec0 = (u32)px0 | ((u32)x << 8) | (soft << 16); /* px0:8 x:8 u:4 v:4 wv:5 */
+            const int adr = active ? (int)((((soft & 15u) >> 1) << 8) | (u32)texture_bits(nb, px0)) : 0x10000 + lane;
             carry_px0 = __shfl_sync(FULL, px0, 31);
 
-            /* ---------------- phase S: one pixel at a time ---------------- */
+            /* ---- bias table (R: NBLIC.c:413-428) and residual fold (:431-447): pixels that share a table
+             * address go in raster order, one per round; different addresses proceed together ---- */
+            int px = 0, sign = 0, y = 0;
+            {
+                const unsigned peers = __match_any_sync(FULL, adr);
+                const int my_turn = __popc(peers & ((1u << lane) - 1u));
+                const int rounds = __reduce_max_sync(FULL, active ? __popc(peers) : 0);
+                for (int r = 0; r < rounds; r++) {
+                    if (active && my_turn == r) {
+                        const int c = sm.ctx[adr];
+                        n_bias_apply(c, px0, px, sign);
+                        const int room = min(px, 255 - px), mag = abs(x - px);
+                        y = mag == 0 ? 0 : (mag <= room ? 2 * mag - ((x >= px) ^ sign) : mag + room);
+                        sm.ctx[adr] = (int16_t)n_bias_learn(c, clampi(x - px0, -127, 127));
+                    }
+                    __syncwarp();
+                }
+            }
+            /* ---- rank mapper (R: NBLIC.c:470-523), same scheme keyed by (px, sign) ---- */
+            int z = y;
+            {
+                const int key = ((px << 1) | sign) * N_RANKS;
+                const bool ranked = active && y < N_RANKS;
+                const unsigned peers = __match_any_sync(FULL, ranked ? key : -1 - lane);
+                const int my_turn = __popc(peers & ((1u << lane) - 1u));
+                const int rounds = __reduce_max_sync(FULL, ranked ? __popc(peers) : 0);
+                for (int r = 0; r < rounds; r++) {
+                    if (ranked && my_turn == r) {
+                        z = RG ? (int)__ldcg(rank + key + y) : (int)rank[key + y];
+                        const int cz = __ldcg(count + key + z) + 1;
+                        bool promoted = false;
+                        if (z > 0) {
+                            const int cp = __ldcg(count + key + z - 1);
+                            if (cp < cz) { /* one adjacent promotion: find the symbol that holds rank z-1 */
+                                const u32 want = (u32)(z - 1) * 0x01010101u;
+                                int other = 0;
+#pragma unroll
+                                for (int q4 = 0; q4 < N_RANKS / 4; q4++) {
+                                    const u32 *wp = reinterpret_cast<const u32 *>(rank + key) + q4;
+                                    const u32 hit = __vcmpeq4(RG ? __ldcg(wp) : *wp, want);
+                                    if (hit) other = 4 * q4 + ((__ffs((int)hit) - 1) >> 3);
+                                }
+                                count[key + z] = cp; count[key + z - 1] = cz;
+                                rank[key + y] = (uint8_t)(z - 1); rank[key + other] = (uint8_t)z;
+                                promoted = true;
+                            }
+                        }
+                        if (!promoted) count[key + z] = cz;
+                    }
+                    __syncwarp();
+                }
+            }
+            const u32 rec0 = soft | ((u32)z << 13); /* u:4 v:4 wv:5 z:8 */
+
+            /* ---------------- phase S: decisions and range coder, one pixel at a time ---------------- */
             const int n_here = min(32, w - j0);
             for (int jj = 0; jj < n_here; jj++) {
                 const u32 r0 = __shfl_sync(FULL, rec0, jj);
-                const int adr_s = (int)__shfl_sync(FULL, adr, jj);
-                const int s_px0 = r0 & 255, s_x = (r0 >> 8) & 255;
-                const int u = (r0 >> 16) & 15, v = (r0 >> 20) & 15, wv = (r0 >> 24) & 31;
-
-                /* bias cancel, residual fold, context update (R: NBLIC.c:413-466) */
-                const int c = sm.ctx[adr_s];
-                int px, sign;
-                n_bias_apply(c, s_px0, px, sign);
-                const int room = min(px, 255 - px), mag = abs(s_x - px);
-                const int y = mag == 0 ? 0 : (mag <= room ? 2 * mag - ((s_x >= px) ^ sign) : mag + room);
-                if (lane == 0) sm.ctx[adr_s] = (int16_t)n_bias_learn(c, clampi(s_x - s_px0, -127, 127));
-
-                const int key = ((px << 1) | sign) * N_RANKS;
-                int my_rank, my_count;
-                coop_rank_fetch<RG>(rank, count, key, lane, my_rank, my_count);
-                const int z = coop_rank_encode(y, my_rank);
-                coop_encode_symbol(rc, sm, forest, k_step, top, ktab, u, v, wv, z, lane);
-                coop_rank_touch_encode(rank, count, key, y, z, lane, my_rank, my_count);
+                coop_encode_symbol(rc, sm, forest, k_step, top, ktab, (int)(r0 & 15u), (int)((r0 >> 4) & 15u), (int)((r0 >> 8) & 31u), (int)(r0 >> 13), lane);
                 __syncwarp();
             }
         }
