@@ -511,14 +511,79 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
                     __syncwarp();
                 }
             }
-            const u32 rec0 = soft | ((u32)z << 13); /* u:4 v:4 wv:5 z:8 */
-
-            /* ---------------- phase S: decisions and range coder, one pixel at a time ---------------- */
+            /* ---- binarisation (R: NBLIC.c:589-679).  Every decision of the block visits two counter nodes; a
+             * node's visits must happen in decision order, visits to different nodes are independent.  The
+             * decisions are flattened (prefix sum of the per-pixel counts), taken 16 at a time with lane
+             * 2*dd + role = visit of decision dd to its main (role 0) / side (role 1) class node, and the
+             * visits advance in match_any rounds like the tables above.  The range coder then walks the 16
+             * (bit, p) pairs.  A block containing an order escape falls back to the per-pixel routine. ---- */
+            const int cu_ = (int)(soft & 15u), wv_ = (int)((soft >> 8) & 31u), k_ = order_of(ktab, cu_);
+            const int cv_ = order_of(ktab, (int)((soft >> 4) & 15u)) == k_ ? (int)((soft >> 4) & 15u) : cu_;
+            const int q_ = z >> k_;
+            const int D_ = active ? q_ + 1 + k_ : 0;
+            const u32 rec0 = (u32)cu_ | ((u32)cv_ << 4) | ((u32)wv_ << 8) | ((u32)z << 13); /* u:4 v:4 wv:5 z:8 */
             const int n_here = min(32, w - j0);
-            for (int jj = 0; jj < n_here; jj++) {
-                const u32 r0 = __shfl_sync(FULL, rec0, jj);
-                coop_encode_symbol(rc, sm, forest, k_step, top, ktab, (int)(r0 & 15u), (int)((r0 >> 4) & 15u), (int)((r0 >> 8) & 31u), (int)(r0 >> 13), lane);
-                __syncwarp();
+            if (__any_sync(FULL, active && q_ >= (256 >> top))) {
+                for (int jj = 0; jj < n_here; jj++) {
+                    const u32 r0 = __shfl_sync(FULL, rec0, jj);
+                    coop_encode_symbol(rc, sm, forest, k_step, top, ktab, (int)(r0 & 15u), (int)((r0 >> 4) & 15u), (int)((r0 >> 8) & 31u), (int)(r0 >> 13), lane);
+                    __syncwarp();
+                }
+                continue;
+            }
+            int off = D_; /* exclusive prefix sum of the decision counts */
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) { const int t = __shfl_up_sync(FULL, off, dlt); if (lane >= dlt) off += t; }
+            const int total = __shfl_sync(FULL, off, 31);
+            off -= D_;
+            for (int base = 0; base < total; base += 16) {
+                const int dd = lane >> 1, role = lane & 1, g = base + dd;
+                const bool valid = g < total;
+                int owner = 0; /* the pixel decision g belongs to: largest lane whose offset is <= g */
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int cand = owner + step;
+                    const int o = __shfl_sync(FULL, off, cand & 31);
+                    if (cand < 32 && o <= g) owner = cand;
+                }
+                const u32 r0 = __shfl_sync(FULL, rec0, owner);
+                const int d = g - __shfl_sync(FULL, off, owner);
+                const int u = (int)(r0 & 15u), v = (int)((r0 >> 4) & 15u), wv = (int)((r0 >> 8) & 31u), zz = (int)(r0 >> 13);
+                const int k = order_of(ktab, u), q = zz >> k;
+                int slot, bit;
+                if (d <= q) { slot = d << k; bit = d < q; }
+                else {
+                    const int t = d - q - 1, kk = max(k - 1 - t, 0);
+                    const int hi_bits = (zz & ((1 << k) - 1)) & ~((2 << kk) - 1);
+                    slot = (q << k) + ((1 + hi_bits + t - __popc(hi_bits)) & ((1 << k) - 1));
+                    bit = (zz >> kk) & 1;
+                }
+                const bool same = u == v;
+                const bool visiting = valid && !(same && role == 1);
+                const int idx = visiting ? (int)sm.fbase[role ? v : u] + slot : -1 - lane;
+                const int weight = role ? wv : N_MIX - wv;
+                const unsigned peers = __match_any_sync(FULL, idx);
+                const int my_turn = __popc(peers & ((1u << lane) - 1u));
+                const int rounds = __reduce_max_sync(FULL, visiting ? __popc(peers) : 0);
+                int p1 = 0;
+                for (int r = 0; r < rounds; r++) {
+                    if (visiting && my_turn == r) {
+                        const u32 c = forest[idx], sc = pair_sum(c);
+                        p1 = node_p1_fast(c, sc);
+                        u32 c2 = learn_packed(c, sc, bit, weight);
+                        if (same) c2 = learn_packed(c2, pair_sum(c2), bit, wv);
+                        forest[idx] = c2;
+                    }
+                    __syncwarp();
+                }
+                const int p_mate = __shfl_xor_sync(FULL, p1, 1);
+                const int pu = role ? p_mate : p1, pv = same ? pu : (role ? p1 : p_mate);
+                const u32 coded = (u32)max((pu * (N_MIX - wv) + pv * wv + N_MIX / 2) >> 5, 1) | ((u32)bit << 12);
+                const int nd = min(16, total - base);
+                for (int e = 0; e < nd; e++) {
+                    const u32 cd = __shfl_sync(FULL, coded, 2 * e);
+                    rc.bit((int)(cd >> 12), cd & 0xfffu);
+                }
             }
         }
     }
