@@ -312,73 +312,71 @@ NB_DEV void coop_encode_symbol(CoopCoder<false> &rc, CoopSmem &sm, u32 *forest, 
 }
 
 /* ---- decoder side of one symbol ----------------------------------------------------------------- */
-/* Returns z, or -1 for a corrupt stream. */
-NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, int k_step, int top, u32 ktab, int u, int v, int wv,
-                              int lane) {
+/* Returns z, or -1 for a corrupt stream.
+ * A class's compacted nodes are laid out so that slot = (unary index << k) + in-order suffix offset; the
+ * walk of one symbol therefore stays inside the aligned 2^k-slot group of its unary index.  The lanes
+ * evaluate a 32-slot window (slot = window + lane: one coalesced load per class), the coder walks the
+ * unary run and the suffix inside it, and the visited lanes then update their counters.  For k <= 2 the whole
+ * class is one window; for k = 3 a second window is needed only when the unary run exceeds 3. */
+NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, int k_step, int top, u32 ktab, int u, int v, int wv, int lane) {
     int k = order_of(ktab, u);
     if (order_of(ktab, v) != k) v = u;
     const int bu = sm.fbase[u], bv = sm.fbase[v];
-    const int n_unary = 256 >> top; /* unary nodes of one tree before the order escape */
-    int q = -1;
-    for (int base = 0; base < n_unary && q < 0; base += 32) {
-        /* every lane evaluates one candidate node of the unary run */
-        const int d = base + lane, slot = d << k;
+    const int n_unary = 256 >> top;  /* unary nodes of one tree before the order escape */
+    const int n_slots = n_unary << k;
+    int q = 0, m = 0, kk = k - 1, z = 0; /* unary index; suffix offset (0 = still in the unary run); remaining suffix bits */
+    bool done = false;
+    while (!done && q < n_unary) {
+        const int w0 = ((q << k) + m) & ~31;
+        const int slot = w0 + lane;
         u32 cu = 0, cv = 0, su = 64, sv = 64, p = 0;
-        if (d < n_unary) { cu = forest[bu + slot]; cv = forest[bv + slot]; su = pair_sum(cu); sv = pair_sum(cv); p = mixed_p(cu, cv, su, sv, wv); }
-        const int lim = min(32, n_unary - base);
-        int stop = -1;
-        for (int dd = 0; dd < lim; dd++) {
-            const u32 pd = __shfl_sync(FULL, p, dd);
-            if (!rc.bit(0, pd)) { stop = dd; break; }
+        if (slot < n_slots) { cu = forest[bu + slot]; cv = forest[bv + slot]; su = pair_sum(cu); sv = pair_sum(cv); p = mixed_p(cu, cv, su, sv, wv); }
+        unsigned visited = 0, ones = 0;
+        while (q < n_unary) {
+            const int cur = (q << k) + m;
+            if ((cur & ~31) != w0) break; /* the unary run left the window */
+            const int ln = cur & 31;
+            const int b = rc.bit(0, __shfl_sync(FULL, p, ln));
+            visited |= 1u << ln; ones |= (u32)b << ln;
+            if (m == 0) { /* unary run */
+                if (b) q++;
+                else { z = q << k; if (k == 0) { done = true; break; } m = 1; }
+            } else {      /* suffix bit of weight 2^kk */
+                if (b) z += 1 << kk;
+                m += b ? (1 << kk) : 1;
+                if (--kk < 0) { done = true; break; }
+            }
         }
-        const int last = stop >= 0 ? stop : lim - 1;
-        if (lane <= last) learn_pair(forest, bu + slot, bv + slot, cu, cv, su, sv, wv, !(stop >= 0 && lane == stop));
-        if (stop >= 0) q = base + stop;
+        if ((visited >> lane) & 1u) learn_pair(forest, bu + slot, bv + slot, cu, cv, su, sv, wv, (int)((ones >> lane) & 1u));
+        __syncwarp();
     }
-    __syncwarp();
-    if (q < 0) { /* order escape: continue one decision at a time in the next order's tree (R: NBLIC.c:658-662) */
-        int uu = (k + 1) * k_step, node = 128;
-        for (;;) {
-            if (uu >= N_CLASSES) return -1;
-            k = order_of(ktab, uu);
-            const int at = sm.fbase[uu] + compact_node(node, top, k);
-            const u32 c = forest[at], sc = pair_sum(c);
-            const int bit = rc.bit(0, mixed_p(c, c, sc, sc, wv));
-            __syncwarp();
-            if (lane == 0) learn_pair(forest, at, at, c, c, sc, sc, wv, bit);
-            __syncwarp();
-            if (!bit) break;
-            node += 1 << top;
-            if (node >= 256) { node >>= 1; uu = (k + 1) * k_step; }
-        }
-        int z = (node >> top) << k;
-        const int k_tree = k;
-        for (node++, k--; k >= 0; k--) {
-            const int at = sm.fbase[uu] + compact_node(node & 255, top, k_tree);
-            const u32 c = forest[at], sc = pair_sum(c);
-            const int bit = rc.bit(0, mixed_p(c, c, sc, sc, wv));
-            __syncwarp();
-            if (lane == 0) learn_pair(forest, at, at, c, c, sc, sc, wv, bit);
-            __syncwarp();
-            if (bit) z += 1 << k;
-            node += bit ? (1 << k) : 1;
-        }
-        return z;
+    if (done) return z;
+    /* order escape: continue one decision at a time in the next order's tree (R: NBLIC.c:658-662) */
+    int uu = (k + 1) * k_step, node = 128;
+    for (;;) {
+        if (uu >= N_CLASSES) return -1;
+        k = order_of(ktab, uu);
+        const int at = sm.fbase[uu] + compact_node(node, top, k);
+        const u32 c = forest[at], sc = pair_sum(c);
+        const int bit = rc.bit(0, mixed_p(c, c, sc, sc, wv));
+        __syncwarp();
+        if (lane == 0) learn_pair(forest, at, at, c, c, sc, sc, wv, bit);
+        __syncwarp();
+        if (!bit) break;
+        node += 1 << top;
+        if (node >= 256) { node >>= 1; uu = (k + 1) * k_step; }
     }
-    int z = q << k;
-    if (k > 0) { /* suffix: lane L in [1, 2^k) is the node reached by the bit prefix spelled by L below its leading 1 */
-        const int L = max(lane, 1), t = 31 - __clz(L), prefix = L ^ (1 << t);
-        const bool valid = lane >= 1 && lane < (1 << k);
-        const int slot = (q << k) + ((1 + (prefix << max(k - t, 0)) + t - __popc(prefix)) & ((1 << k) - 1));
-        u32 cu = 0, cv = 0, su = 64, sv = 64, p = 0;
-        if (valid) { cu = forest[bu + slot]; cv = forest[bv + slot]; su = pair_sum(cu); sv = pair_sum(cv); p = mixed_p(cu, cv, su, sv, wv); }
-        int cur = 1;
-        for (int s = 0; s < k; s++) {
-            const u32 pd = __shfl_sync(FULL, p, cur);
-            cur = 2 * cur + rc.bit(0, pd);
-        }
-        z += cur - (1 << k);
-        if (valid && (cur >> (k - t)) == lane) learn_pair(forest, bu + slot, bv + slot, cu, cv, su, sv, wv, (cur >> (k - t - 1)) & 1);
+    z = (node >> top) << k;
+    const int k_tree = k;
+    for (node++, k--; k >= 0; k--) {
+        const int at = sm.fbase[uu] + compact_node(node & 255, top, k_tree);
+        const u32 c = forest[at], sc = pair_sum(c);
+        const int bit = rc.bit(0, mixed_p(c, c, sc, sc, wv));
+        __syncwarp();
+        if (lane == 0) learn_pair(forest, at, at, c, c, sc, sc, wv, bit);
+        __syncwarp();
+        if (bit) z += 1 << k;
+        node += bit ? (1 << k) : 1;
     }
     return z;
 }
