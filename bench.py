@@ -326,10 +326,17 @@ def main():
     sm_mhz_max = float(peaks.get("sm_max_mhz", 1965.0))
     issue_peak = sm_count * 4 * 32 * sm_mhz_max * 1e6  # lane-issue slots / s
     issue_dom = B * npx / dom_s * SLOTS_PER_PIXEL[EFFORT]
+    traffic, traffic_note = None, "no ncu capture on record"
+    try:  # dram bytes per pixel of the same kernel from the committed ncu --set full capture, scaled to this launch
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["e1_decode" if dom_is_dec else "e1_encode_lossless"]
+        traffic = int(cap["dram_bytes_per_pixel"] * B * npx)
+        traffic_note = "dram__bytes_read+write per pixel of the ncu capture (%s) x pixels of this launch; above the algorithmic bytes because the per-stream rank/frequency tables (50 KB x resident streams) exceed L2" % cap["capture"]
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": "coop_nblic_kernel<effort 1, %s>" % ("decode" if dom_is_dec else "lossless encode"),
         "achieved": round(alg_bytes / dom_s / 1e9, 3), "peak": hbm_peak, "unit": "GB/s",
-        "frac": round(alg_bytes / dom_s / 1e9 / hbm_peak, 6), "traffic": None, "peak_source": peak_src,
+        "frac": round(alg_bytes / dom_s / 1e9 / hbm_peak, 6), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
         "kernel_ms": round(1e3 * dom_s, 3), "encode_kernel_ms": round(1e3 * enc_s, 3), "decode_kernel_ms": round(1e3 * dec_s, 3),
         "algorithmic_bytes_per_launch": int(alg_bytes),
         "note": "the path is bound by dependent integer issue, not HBM or tensor throughput (SURVEY.md 8(d)): see `issue`",

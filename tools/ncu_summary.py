@@ -3,6 +3,8 @@ usage: python tools/ncu_summary.py REPORT.ncu-rep PIXELS [kernel-substring] [top
 import csv, io, subprocess, sys
 rep, pixels = sys.argv[1], float(sys.argv[2])
 kfilter = sys.argv[3] if len(sys.argv) > 3 else ""
+norm = lambda t: (t or "").replace("(int)", "").replace("(bool)", "").replace("true", "1").replace("false", "0").replace(" ", "")
+kfilter = norm(kfilter)
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -12,7 +14,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__r
         "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "smsp__average_warp_latency_per_inst_issued.ratio"]
 for r in rows[2:]:
-    if kfilter not in r[hdr.index("Kernel Name")]:
+    if kfilter not in norm(r[hdr.index("Kernel Name")]):
         continue
     print("=" * 100)
     for w in want:
@@ -38,7 +40,7 @@ for r in csv.reader(io.StringIO(src)):
     if r[0] == "File Path": cur_file = r[1]; continue
     if r[0] == "Function Name": cur_fn = r[1]; continue
     if r[0] == "Line No": h2 = r; continue
-    if h2 and r[0].isdigit() and len(r) > 8 and kfilter in (cur_fn or ""):
+    if h2 and r[0].isdigit() and len(r) > 8 and kfilter in norm(cur_fn):
         d = dict(zip(h2, r))
         try:
             out.append((cur_file.split("/")[-1], int(r[0]), int(d["Instructions Executed"]), int(d["# Samples"]), r[1].strip()[:100]))
