@@ -208,16 +208,19 @@ NB_DEV u32 learn_packed(u32 c, u32 s, int bit, int weight) {
     return c;
 }
 NB_DEV u32 pair_sum(u32 c) { return (c & 0xffffu) + (c >> 16); }
-/* floor(4096 * n1 / s) without the integer divide: float estimate (error < 2e-3), multiply back,
- * correct by one.  s <= 8224 and 4096 * n1 < 2^26 with 12 trailing zero bits, so both convert exactly. */
+/* floor(4096 * n1 / s) without the integer divide and without the conversion pipe: n1 and s (< 2^23) become
+ * floats by the 2^23 mantissa trick, the quotient estimate (error < 2e-3) is rounded to an integer by the
+ * 1.5 * 2^23 trick, then multiply back and correct by one.  Only the reciprocal itself uses the SFU. */
 NB_DEV int node_p1_fast(u32 packed, u32 s) {
-    const u32 a = (packed >> 16) << 12;
+    const u32 n1 = packed >> 16;
+    const float fn1 = __uint_as_float(0x4B000000u | n1) - 8388608.0f;
+    const float fs = __uint_as_float(0x4B000000u | s) - 8388608.0f;
     float rcp;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(__uint2float_rn(s)));
-    u32 q = __float2uint_rz(__uint2float_rn(a) * rcp);
-    const int r = (int)a - (int)(q * s);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(fs));
+    int q = (int)(__float_as_uint(fn1 * 4096.0f * rcp + 12582912.0f) - 0x4B400000u); /* nearest integer to the estimate */
+    const int r = (int)(n1 << 12) - q * (int)s;
     if (r < 0) q--; else if (r >= (int)s) q++;
-    return (int)q;
+    return q;
 }
 /* R: NBLIC.c:627-631.  Both p1 are <= 4095 (n0 >= 1), so only the lower clip can act. */
 NB_DEV u32 mixed_p(u32 cu, u32 cv, u32 su, u32 sv, int wv) {
