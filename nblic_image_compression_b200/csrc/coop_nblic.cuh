@@ -20,8 +20,10 @@
  *                                              through 128-byte lines held one word per lane
  *                                                                                     R: NBLIC.c:527-586
  *
- * Pixels whose Golomb code escapes to the next order (0.1-0.5 %) finish in the sequential routine of
- * codec_core.cuh on the leader lane.
+ * The lossless encoder goes further: its bias table, rank mappers and counter forest advance for 32
+ * pixels at once in __match_any rounds (only entries that collide are ordered), see
+ * coop_e1_encode_lossless.  Pixels whose Golomb code escapes to the next order (0.1-0.5 %) run their
+ * decisions one by one, warp-uniform.
  */
 #pragma once
 #include "codec_core.cuh"
