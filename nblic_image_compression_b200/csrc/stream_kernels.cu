@@ -348,7 +348,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-std::string g_create_error;
+thread_local std::string g_create_error; /* message of a failed nblic_b200_create on this thread */
 
 } /* namespace */
 
@@ -784,8 +784,17 @@ int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *imag
     const int n_chunks = (n + chunk_n - 1) / chunk_n;
     auto upload = [&](int k) -> int {
         const int lo = k * chunk_n, hi = std::min(n, lo + chunk_n);
-        for (int i = lo; i < hi; i++)
-            if (dims_fine(i)) CK(cudaMemcpyAsync(d_pix + pix_off[(size_t)i], images[i], (size_t)heights[i] * widths[i], cudaMemcpyHostToDevice, c->copy));
+        for (int i = lo; i < hi;) { /* images that are adjacent on the host and on the device travel as one copy */
+            if (!dims_fine(i)) { i++; continue; }
+            size_t bytes = (size_t)heights[i] * widths[i];
+            int j = i + 1;
+            while (j < hi && dims_fine(j) && images[j] == images[i] + bytes && pix_off[(size_t)j] == pix_off[(size_t)i] + bytes) {
+                bytes += (size_t)heights[j] * widths[j];
+                j++;
+            }
+            CK(cudaMemcpyAsync(d_pix + pix_off[(size_t)i], images[i], bytes, cudaMemcpyHostToDevice, c->copy));
+            i = j;
+        }
         CK(cudaEventRecord(c->ev_copy[k & 1], c->copy));
         return 0;
     };
@@ -879,10 +888,19 @@ int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *stre
         coder_ms += c->coder_ms;
         for (int i = lo; i < hi; i++) {
             if (st[(size_t)i] == NBLIC_B200_OK) st[(size_t)i] = dev_st[(size_t)i];
-            if (st[(size_t)i] == NBLIC_B200_OK)
-                CK(cudaMemcpyAsync(images[i], (uint8_t *)c->pixels.p + pix_off[(size_t)i], (size_t)peeks[(size_t)i].h * peeks[(size_t)i].w, cudaMemcpyDeviceToHost, c->copy));
             if (status) status[i] = st[(size_t)i];
             failed += st[(size_t)i] != NBLIC_B200_OK;
+        }
+        for (int i = lo; i < hi;) { /* rasters that are adjacent on the device and on the host travel as one copy */
+            if (st[(size_t)i] != NBLIC_B200_OK) { i++; continue; }
+            size_t bytes = (size_t)peeks[(size_t)i].h * peeks[(size_t)i].w;
+            int j = i + 1;
+            while (j < hi && st[(size_t)j] == NBLIC_B200_OK && images[j] == images[i] + bytes && pix_off[(size_t)j] == pix_off[(size_t)i] + bytes) {
+                bytes += (size_t)peeks[(size_t)j].h * peeks[(size_t)j].w;
+                j++;
+            }
+            CK(cudaMemcpyAsync(images[i], (uint8_t *)c->pixels.p + pix_off[(size_t)i], bytes, cudaMemcpyDeviceToHost, c->copy));
+            i = j;
         }
     }
     c->coder_ms = coder_ms;

@@ -300,6 +300,30 @@ def test_extreme_shapes_vs_oracle(api, codec, oracle):
         _check_batch(api, codec, oracle, small, effort, near, api.MAP_AUTO)
 
 
+def test_context_reuse_and_concurrent_contexts(api, oracle):
+    """Scratch buffers grow and are reused across calls of different shapes; two contexts on two host
+    threads code at the same time (the reference's functions are re-entrant)."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(5)
+
+    def work(seed):
+        c = api.Codec(0)
+        ok = True
+        for rnd in range(6):
+            n = int(rng.integers(1, 40))
+            imgs = [gen(int(rng.integers(1, 70)), int(rng.integers(1, 90)), seed * 1000 + rnd * 50 + k) for k in range(n)]
+            effort, near = [(0, 0), (1, 0), (1, 2), (2, 0), (3, 1), (1, 0)][rnd]
+            streams, recs, status = c.encode_batch(imgs, near, effort, want_recon=near > 0)
+            exp = [_oracle_enc(oracle, im, effort, near) for im in imgs]
+            ok &= all(s == e[0] for s, e in zip(streams, exp))
+            ok &= all(d is not None and np.array_equal(d[0], e[1]) for d, e in zip(c.decode_batch(streams), exp))
+        c.close()
+        return ok
+
+    with ThreadPoolExecutor(2) as pool:
+        assert all(pool.map(work, [1, 2]))
+
+
 def test_full_size_round_trip_properties(api, codec):
     """BASELINE.json sizes the oracle cannot finish quickly: encode -> decode identity, near bound."""
     import torch

@@ -66,6 +66,20 @@ def test_sniff_rejects_foreign_streams_without_cuda(lib):
     assert api.legacy.nblic_decompress(b"Q0.2" + bytes(64)) is None
 
 
+def test_bench_reference_arm_emits_the_contract_line():
+    """bench.py --impl reference needs no GPU: one JSON line with the base contract's keys."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, check=True).stdout.strip().splitlines()[-1]
+    line = json.loads(out)
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+
+
 def test_plan_shards_properties():
     from nblic_image_compression_b200.shard import plan_shards
     rng = np.random.default_rng(0)
