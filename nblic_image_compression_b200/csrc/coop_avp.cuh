@@ -121,11 +121,14 @@ NB_DEV void avp_predict_pair(AvpSmem &sm, const i64 (&E)[AvpGeom<N>::NS], const 
     i64 *b = sm.ds[sys] + 1, *A = sm.ds[sys] + 1 + N;
     bool alive = true; /* uniform inside a half-warp */
 
-#pragma unroll
+    /* For n = 10 the k loops stay rolled: unrolled, that solver alone is ~90 KB of SASS and every pixel streams
+     * it through the 32 KB instruction cache (ncu: no_instruction was the top stall of the effort-3 kernel;
+     * rolled +4 %).  The n = 6 solver is small enough to profit from unrolling (+5 %). */
+    constexpr int kUnroll = N > 6 ? 1 : N;
+#pragma unroll kUnroll
     for (int k = 0; k + 1 < N; k++) { /* forward elimination with partial pivoting */
         int piv = k;
         i64 best = labs64(A[k * N + k]);
-#pragma unroll
         for (int r = k + 1; r < N; r++) {
             const i64 m = labs64(A[r * N + k]);
             if (m > best) { best = m; piv = r; } /* first row of maximal magnitude */
@@ -140,10 +143,10 @@ NB_DEV void avp_predict_pair(AvpSmem &sm, const i64 (&E)[AvpGeom<N>::NS], const 
         if (d == 0) alive = false;
         if (alive) {
             const Rcp64 rc = make_rcp(d);
-            constexpr int dummy = 0; (void)dummy;
             const int W = N - k, cnt = (N - 1 - k) * W; /* per row: columns k+1..N-1, then b */
+            const u32 w_magic = 65536u / (u32)W + 1u;   /* e / W == (e * w_magic) >> 16 for e < 128 */
             for (int e = hl; e < cnt; e += 16) {
-                const int r = k + 1 + e / W, cc = e % W;
+                const int ro = (int)(((u32)e * w_magic) >> 16), cc = e - ro * W, r = k + 1 + ro;
                 const i64 f = A[r * N + k];
                 if (f != 0) {
                     if (cc < W - 1) { const int c = k + 1 + cc; A[r * N + c] -= div_rcp(wmul(A[k * N + c], f), rc); }
@@ -153,7 +156,7 @@ NB_DEV void avp_predict_pair(AvpSmem &sm, const i64 (&E)[AvpGeom<N>::NS], const 
         }
         __syncwarp();
     }
-#pragma unroll
+#pragma unroll kUnroll
     for (int k = N - 1; k > 0; k--) { /* back substitution on b */
         const i64 d = A[k * N + k];
         if (d == 0) alive = false;
