@@ -44,16 +44,28 @@ NB_DEV Rcp64 make_rcp(i64 d) {
     rc.r = 1.0 / __ull2double_rn(rc.ud);
     return rc;
 }
-/* trunc(n / d), n and d any int64 with d != 0 (two's-complement wrap like x86 idiv, minus the trap). */
+/* trunc(n / d), n and d any int64 with d != 0 (two's-complement wrap like x86 idiv, minus the trap).
+ * Fast path: the fp64 estimate has relative error < 2^-51, so for quotients below 2^50 its truncation is
+ * within one of the answer.  Larger quotients (small pivots, seen on near-lossless reconstructions) take a
+ * second estimate on the remainder, which brings the error back under one before the same correction.
+ * Anything else (|d| >= 2^50) uses the plain 64-bit divide. */
 NB_DEV i64 div_rcp(i64 n, const Rcp64 &rc) {
     const bool nneg = n < 0;
     const u64 un = nneg ? (u64)0 - (u64)n : (u64)n;
     const double qf = __ull2double_rn(un) * rc.r;
     u64 q;
-    if (qf < 1125899906842624.0 /* 2^50 */ && rc.ud < (1ull << 61)) {
-        /* relative error of qf < 2^-51, so trunc(qf) is within one of the quotient */
+    if (rc.ud < (1ull << 49)) {
         q = __double2ull_rz(qf);
-        i64 r = (i64)(un - q * rc.ud);
+        i64 r = (i64)(un - q * rc.ud); /* |r| <= (2^-51 * un / ud + 1) * ud < 2^63: no wrap */
+        if (qf >= 1125899906842624.0 /* 2^50 */) { /* refine: |r| / ud <= 2^13 + 1, its estimate is within one */
+            const bool rneg = r < 0;
+            const u64 ur = rneg ? (u64)0 - (u64)r : (u64)r;
+            const u64 q2 = __double2ull_rz(__ull2double_rn(ur) * rc.r);
+            q = rneg ? q - q2 : q + q2;
+            r = (i64)(un - q * rc.ud); /* now in (-2 ud, 2 ud) */
+            if (r < 0) { q--; r += (i64)rc.ud; }
+            if (r >= (i64)rc.ud) { q++; r -= (i64)rc.ud; }
+        }
         if (r < 0) { q--; r += (i64)rc.ud; }
         if (r >= (i64)rc.ud) { q++; }
     } else {

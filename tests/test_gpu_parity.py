@@ -144,8 +144,17 @@ def test_exact_int64_division(codec):
             nums.append(n * sn); dens.append(np.where(d == 0, 1, d) * sd)
     edge = np.array([0, 1, -1, 2, -2, 3, 2**53 - 1, 2**53, 2**53 + 1, -(2**53) - 1, 2**62, -(2**62), 2**63 - 1, -(2**63) + 1, 4096, 65536, 65535], dtype=np.int64)
     nums.append(np.repeat(edge, len(edge))); dens.append(np.tile(np.where(edge == 0, 7, edge), len(edge)))
+    # huge quotients (tiny divisors): the two-step estimate of div_rcp
+    for bits_d in (1, 2, 3, 7, 12):
+        n = rng.integers(1 << 55, (1 << 63) - 1, size=2000, dtype=np.int64) * (rng.integers(0, 2, size=2000) * 2 - 1)
+        d = rng.integers(1, 1 << bits_d, size=2000, dtype=np.int64) * (rng.integers(0, 2, size=2000) * 2 - 1)
+        nums.append(n); dens.append(d)
     # near-multiples: n = q*d + r with r in {-1, 0, 1, d-1}
     q = rng.integers(0, 1 << 40, size=4000, dtype=np.int64); d = rng.integers(1, 1 << 22, size=4000, dtype=np.int64)
+    for r in (-1, 0, 1):
+        nums.append(q * d + r); dens.append(d)
+    nums.append(q * d + d - 1); dens.append(d)
+    q = rng.integers(1 << 52, 1 << 58, size=4000, dtype=np.int64); d = rng.integers(1, 1 << 5, size=4000, dtype=np.int64)
     for r in (-1, 0, 1):
         nums.append(q * d + r); dens.append(d)
     nums.append(q * d + d - 1); dens.append(d)
