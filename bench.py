@@ -326,9 +326,11 @@ def main():
     sm_mhz_max = float(peaks.get("sm_max_mhz", 1965.0))
     issue_peak = sm_count * 4 * 32 * sm_mhz_max * 1e6  # lane-issue slots / s
     issue_dom = B * npx / dom_s * SLOTS_PER_PIXEL[EFFORT]
-    traffic, traffic_note = None, "no ncu capture on record"
+    traffic, traffic_note, pipes = None, "no ncu capture on record", None
     try:  # dram bytes per pixel of the same kernel from the committed ncu --set full capture, scaled to this launch
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["e1_decode" if dom_is_dec else "e1_encode_lossless"]
+        figures = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        pipes = figures.get("pipes", {}).get("coop_nblic_kernel<0, 2, 1>" if dom_is_dec else "coop_nblic_kernel<0, 0, 1>")
+        cap = figures["e1_decode" if dom_is_dec else "e1_encode_lossless"]
         traffic = int(cap["dram_bytes_per_pixel"] * B * npx)
         traffic_note = "dram__bytes_read+write per pixel of the ncu capture (%s) x pixels of this launch; above the algorithmic bytes because the per-stream rank/frequency tables (50 KB x resident streams) exceed L2" % cap["capture"]
     except Exception:
@@ -341,7 +343,9 @@ def main():
         "algorithmic_bytes_per_launch": int(alg_bytes),
         "note": "the path is bound by dependent integer issue, not HBM or tensor throughput (SURVEY.md 8(d)): see `issue`",
         "issue": {"unit": "T lane-issue-slots/s", "slots_per_pixel": SLOTS_PER_PIXEL[EFFORT], "achieved": round(issue_dom / 1e12, 4),
-                  "peak": round(issue_peak / 1e12, 3), "frac": round(issue_dom / issue_peak, 6)},
+                  "peak": round(issue_peak / 1e12, 3), "frac": round(issue_dom / issue_peak, 6),
+                  "ncu_pipes_pct_of_peak": pipes,
+                  "ncu_note": "pipe utilisation of the same kernel from the committed ncu capture (profiles/r01_final_*.txt): the integer ALU pipe is the binding unit"},
     }
 
     cpu = None
