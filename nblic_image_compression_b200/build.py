@@ -45,7 +45,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for s in SOURCES_CU:
         o = os.path.join(objdir, s + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("NBLIC_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
