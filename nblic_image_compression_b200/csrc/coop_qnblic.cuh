@@ -23,15 +23,20 @@
 
 namespace nblic {
 
-struct QCoopSmem {
+struct QCoopSmem { /* encoder */
     int ctx[Q_CTX_ENTRIES]; /* 12 KB bias-cancel table                                           */
     u32 tab[Q_TAB_ENTRIES]; /* 12 KB counts, then freq | cumulative << 16                        */
-    PixRec rec[32];         /*  1 KB decoder: phase-P records                                    */
+};
+enum { Q_CUM_STRIDE = 258 }; /* 257 cumulative frequencies per class (freq = difference), padded to 4 bytes */
+struct QDecSmem { /* decoder: 19.2 KB instead of 25 KB, 11 instead of 8 resident streams per SM */
+    int ctx[Q_CTX_ENTRIES];                 /* 12 KB bias-cancel table                            */
+    uint16_t cum[Q_CLASSES * Q_CUM_STRIDE]; /*  6 KB cumulative frequencies, cum[256] = 2^15      */
+    PixRec rec[32];                         /*  1 KB phase-P records (and scratch while the histograms are parsed) */
 };
 
 /* rows 0 and 1 (and any row of a sequential fallback): the reference loop, warp-uniform, leader stores */
-template <bool DEC, class OnPixel>
-NB_DEV void q_serial_row(const uint8_t *img, int w, int i, QCoopSmem &sm, int lane, OnPixel on_pixel) {
+template <bool DEC, class Smem, class OnPixel>
+NB_DEV void q_serial_row(const uint8_t *img, int w, int i, Smem &sm, int lane, OnPixel on_pixel) {
     Nb nb;
     int err = 0;
     sample_positional(img, w, i, 0, nb);
@@ -183,12 +188,12 @@ struct WordReader {
     }
 };
 
-__device__ void coop_q_decode(const uint16_t *in, u32 avail, uint8_t *img, int h, int w, QCoopSmem &sm, int lane) {
+__device__ void coop_q_decode(const uint16_t *in, u32 avail, uint8_t *img, int h, int w, QDecSmem &sm, int lane) {
     for (int k = lane; k < Q_CTX_ENTRIES; k += 32) sm.ctx[k] = 0;
     u32 rd = 4;
-    if (lane == 0) { /* the 12 histogram descriptions are one sequential code stream.  R: QNBLIC.c:415-459 */
-        for (int c = 0; c < Q_CLASSES; c++) {
-            u32 *hist = sm.tab + c * 256;
+    u32 *hist = reinterpret_cast<u32 *>(sm.rec); /* 256 words of scratch */
+    for (int c = 0; c < Q_CLASSES; c++) { /* the 12 histogram descriptions are one sequential code stream.  R: QNBLIC.c:415-459 */
+        if (lane == 0) {
             for (int k = 0; k < 256; k++) hist[k] = 0;
             u32 pos = 0, sum = 0;
 #define Q_NEXT_() (rd < avail ? (u32)in[rd++] : (rd++, 0u))
@@ -208,11 +213,13 @@ __device__ void coop_q_decode(const uint16_t *in, u32 avail, uint8_t *img, int h
             }
 #undef Q_PUSH_
 #undef Q_NEXT_
+            u32 acc = 0; /* R: QNBLIC.c:290-295; clipped so a malformed table cannot leave 16 bits */
+            for (int k = 0; k < 256; k++) { sm.cum[c * Q_CUM_STRIDE + k] = (uint16_t)min(acc, (u32)Q_NORM_SUM); acc += hist[k]; }
+            sm.cum[c * Q_CUM_STRIDE + 256] = (uint16_t)min(acc, (u32)Q_NORM_SUM);
         }
+        __syncwarp();
     }
     rd = __shfl_sync(FULL, rd, 0);
-    __syncwarp();
-    if (lane < Q_CLASSES) q_pack_cumulative(sm.tab + lane * 256);
     __syncwarp();
 
     WordReader words;
@@ -221,13 +228,13 @@ __device__ void coop_q_decode(const uint16_t *in, u32 avail, uint8_t *img, int h
 
     auto decode_symbol = [&](int cls) -> int { /* R: QNBLIC.c:262-274 with the LUT replaced by two ballots */
         const u32 slot = state & (Q_NORM_SUM - 1);
-        const u32 *tab = sm.tab + cls * 256;
-        const unsigned coarse = __ballot_sync(FULL, (tab[8 * lane] >> 16) <= slot);
+        const uint16_t *cum = sm.cum + cls * Q_CUM_STRIDE;
+        const unsigned coarse = __ballot_sync(FULL, (u32)cum[8 * lane] <= slot);
         const int c8 = 8 * (__popc(coarse) - 1);
-        const unsigned fine = __ballot_sync(FULL, lane < 8 && (tab[c8 + (lane & 7)] >> 16) <= slot);
+        const unsigned fine = __ballot_sync(FULL, lane < 8 && (u32)cum[c8 + (lane & 7)] <= slot);
         const int y = c8 + __popc(fine) - 1;
-        const u32 e = tab[y];
-        state = (state >> Q_NORM_BITS) * (e & 0xffffu) + slot - (e >> 16);
+        const u32 base = cum[y], freq = (u32)cum[y + 1] - base;
+        state = (state >> Q_NORM_BITS) * freq + slot - base;
         if (state < (1u << 16)) state = (state << 16) | words.get();
         return y;
     };

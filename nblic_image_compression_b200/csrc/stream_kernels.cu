@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -198,14 +199,14 @@ __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *
  * shared memory. */
 template <bool DEC>
 __global__ void __launch_bounds__(32) coop_q_kernel(Task *tasks, const int *order, int n_order, int *queue) {
-    __shared__ QCoopSmem sm;
+    __shared__ typename std::conditional<DEC, QDecSmem, QCoopSmem>::type sm;
     const int lane = threadIdx.x;
     for (;;) {
         int pos = lane == 0 ? atomicAdd(queue, 1) : 0;
         pos = __shfl_sync(0xffffffffu, pos, 0);
         if (pos >= n_order) break;
         Task &t = tasks[order[pos]];
-        if (DEC) coop_q_decode(reinterpret_cast<const uint16_t *>(t.slot), t.slot_cap / 2, t.rec, t.h, t.w, sm, lane);
+        if constexpr (DEC) coop_q_decode(reinterpret_cast<const uint16_t *>(t.slot), t.slot_cap / 2, t.rec, t.h, t.w, sm, lane);
         else {
             u32 head = 0, tail = 0;
             const bool ok = coop_q_encode(t.src, t.h, t.w, reinterpret_cast<uint16_t *>(t.slot), t.slot_cap / 2, t.sym, sm, lane, head, tail);
