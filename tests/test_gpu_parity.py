@@ -309,6 +309,40 @@ def test_extreme_shapes_vs_oracle(api, codec, oracle):
         _check_batch(api, codec, oracle, small, effort, near, api.MAP_AUTO)
 
 
+def test_random_fuzz_vs_checker(api, codec, oracle):
+    """Mixed random batches: sizes 1..96 x 1..130, four image statistics, every effort, near 0..9, compared
+    with the unmodified reference when it is built (oracle/_ref), else with the oracle."""
+    from cpu_codecs import Ref
+    chk = Ref() if Ref.available() else oracle
+    rng = np.random.default_rng(2024)
+    codec.set_mapping(api.MAP_AUTO)
+    for trial in range(12):
+        imgs = []
+        for k in range(24):
+            h, w = int(rng.integers(1, 97)), int(rng.integers(1, 131))
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                im = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+            elif kind == 1:
+                im = gen(h, w, 1000 * trial + k)
+            elif kind == 2:
+                im = (rng.integers(0, 2, size=(h, w)) * int(rng.integers(1, 256))).astype(np.uint8)
+            else:
+                im = np.clip(np.cumsum(rng.normal(0, 6, size=(h, w)), axis=1) + np.cumsum(rng.normal(0, 6, size=(h, 1)), axis=0) + 128, 0, 255).astype(np.uint8)
+            imgs.append(im)
+        effort = trial % 4
+        near = 0 if effort == 0 else int(rng.integers(0, 10))
+        streams, recs, status = codec.encode_batch(imgs, near, effort, want_recon=near > 0)
+        assert all(s == api.OK for s in status)
+        exp = [(chk.q_encode(im), im) if effort == 0 else chk.n_encode(im, near, effort)[:2] for im in imgs]
+        for k, (s, e) in enumerate(zip(streams, exp)):
+            assert s == e[0], (trial, effort, near, k, imgs[k].shape)
+            if near:
+                assert np.array_equal(recs[k], e[1]), (trial, effort, near, k)
+        for k, (d, e) in enumerate(zip(codec.decode_batch([e[0] for e in exp]), exp)):
+            assert d is not None and np.array_equal(d[0], e[1]), (trial, effort, near, k)
+
+
 def test_context_reuse_and_concurrent_contexts(api, oracle):
     """Scratch buffers grow and are reused across calls of different shapes; two contexts on two host
     threads code at the same time (the reference's functions are re-entrant)."""
