@@ -332,30 +332,41 @@ NB_DEV int coop_decode_symbol(CoopCoder<true> &rc, CoopSmem &sm, u32 *forest, in
     const int bu = sm.fbase[u], bv = sm.fbase[v];
     const int n_unary = 256 >> top;  /* unary nodes of one tree before the order escape */
     const int n_slots = n_unary << k;
-    int q = 0, m = 0, kk = k - 1, z = 0; /* unary index; suffix offset (0 = still in the unary run); remaining suffix bits */
+    int q = 0, z = 0;
     bool done = false;
     while (!done && q < n_unary) {
-        const int w0 = ((q << k) + m) & ~31;
+        const int w0 = (q << k) & ~31;
         const int slot = w0 + lane;
         u32 cu = 0, cv = 0, su = 64, sv = 64, p = 0;
         if (slot < n_slots) { cu = forest[bu + slot]; cv = forest[bv + slot]; su = pair_sum(cu); sv = pair_sum(cv); p = mixed_p(cu, cv, su, sv, wv); }
-        unsigned visited = 0, ones = 0;
-        while (q < n_unary) {
-            const int cur = (q << k) + m;
-            if ((cur & ~31) != w0) break; /* the unary run left the window */
-            const int ln = cur & 31;
-            const int b = rc.bit(0, __shfl_sync(FULL, p, ln));
-            visited |= 1u << ln; ones |= (u32)b << ln;
-            if (m == 0) { /* unary run */
-                if (b) q++;
-                else { z = q << k; if (k == 0) { done = true; break; } m = 1; }
-            } else {      /* suffix bit of weight 2^kk */
-                if (b) z += 1 << kk;
-                m += b ? (1 << kk) : 1;
-                if (--kk < 0) { done = true; break; }
-            }
+        /* unary run inside the window: nodes q << k */
+        const int q_first = q;
+        bool zero_seen = false;
+        while (q < n_unary && ((q << k) & ~31) == w0) {
+            if (!rc.bit(0, __shfl_sync(FULL, p, (q << k) & 31))) { zero_seen = true; break; }
+            q++;
         }
-        if ((visited >> lane) & 1u) learn_pair(forest, bu + slot, bv + slot, cu, cv, su, sv, wv, (int)((ones >> lane) & 1u));
+        /* lane-side view of the run: my slot is unary node uq iff its low k bits are zero */
+        const int uq = slot >> k;
+        bool visited = (slot & ((1 << k) - 1)) == 0 && uq >= q_first && (zero_seen ? uq <= q : uq < q);
+        int my_bit = uq < q;
+        if (zero_seen) {
+            z = q << k;
+            if (k > 0) { /* suffix: stays inside the aligned 2^k-slot group of q, hence inside this window */
+                int m = 1;
+                unsigned path = 0, ones = 0;
+                for (int kk = k - 1; kk >= 0; kk--) {
+                    const int ln = ((q << k) + m) & 31;
+                    const int b = rc.bit(0, __shfl_sync(FULL, p, ln));
+                    path |= 1u << ln; ones |= (u32)b << ln;
+                    z += b << kk;
+                    m += b ? (1 << kk) : 1;
+                }
+                if ((path >> lane) & 1u) { visited = true; my_bit = (int)((ones >> lane) & 1u); }
+            }
+            done = true;
+        }
+        if (visited) learn_pair(forest, bu + slot, bv + slot, cu, cv, su, sv, wv, my_bit);
         __syncwarp();
     }
     if (done) return z;
