@@ -160,9 +160,11 @@ NB_DEV void avp_predict_pair(AvpSmem &sm, const i64 (&E)[AvpGeom<N>::NS], const 
             for (int e = hl; e < cnt; e += 16) {
                 const int ro = (int)(((u32)e * w_magic) >> 16), cc = e - ro * W, r = k + 1 + ro;
                 const i64 f = A[r * N + k];
-                if (f != 0) {
-                    if (cc < W - 1) { const int c = k + 1 + cc; A[r * N + c] -= div_rcp(wmul(A[k * N + c], f), rc); }
-                    else b[r] -= div_rcp(wmul(b[k], f), rc);
+                if (f != 0) { /* one call site for both kinds of entry: the two would otherwise run one after the other */
+                    const bool in_a = cc < W - 1;
+                    i64 *own = in_a ? &A[r * N + k + 1 + cc] : &b[r];
+                    const i64 above = in_a ? A[k * N + k + 1 + cc] : b[k];
+                    *own -= div_rcp(wmul(above, f), rc);
                 }
             }
         }
@@ -205,10 +207,13 @@ NB_DEV void avp_learn_coop(AvpSmem &sm, i64 (&E)[AvpGeom<N>::NS], i64 *Bj, int x
     for (int s = 0; s < NS; s++) {
         const int k = lane + 32 * s;
         if (k < M) {
-            i64 t;
-            if (k == 0) t = s_now;
-            else if (k <= N) t = div_rcp(wshl(wmul(xc, (i64)sm.vec[k - 1]), 28) + half, rc);
-            else { const int idx = k - 1 - N; t = div_rcp(wshl(wmul((i64)sm.vec[idx / N], (i64)sm.vec[idx % N]), 18) + half, rc); }
+            i64 t = s_now;
+            if (k > 0) { /* b: x' * v_r << 28; A: v_r * v_c << 18 -- one shared division */
+                const int idx = k - 1 - N; /* >= 0 for the A block */
+                const i64 left = k <= N ? xc : (i64)sm.vec[idx / N];
+                const i64 right = (i64)sm.vec[k <= N ? k - 1 : idx % N];
+                t = div_rcp(wshl(wmul(left, right), k <= N ? 28 : 18) + half, rc);
+            }
             const i64 nb = (k == 0 ? avp_decay(Bj[k], 0) : avp_decay(Bj[k], 1)) + t;
             Bj[k] = nb;
             E[s] = (k == 0 ? avp_decay(E[s], 0) : avp_decay(E[s], 1)) + nb;
