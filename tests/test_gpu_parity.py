@@ -343,6 +343,33 @@ def test_random_fuzz_vs_checker(api, codec, oracle):
             assert d is not None and np.array_equal(d[0], e[1]), (trial, effort, near, k)
 
 
+def test_corrupt_streams_never_fault(api, codec):
+    """Bit flips, garbage payloads and truncation behind a valid header: the decoders must stay inside
+    their buffers and return (a raster or a CORRUPT / BAD_HEADER verdict) -- the reference reads blindly."""
+    rng = np.random.default_rng(77)
+    imgs = [gen(int(rng.integers(4, 40)), int(rng.integers(4, 40)), 900 + k) for k in range(6)]
+    bad = []
+    for effort, near in [(0, 0), (1, 0), (1, 4), (2, 0), (3, 2)]:
+        for s in codec.encode_batch(imgs, near, effort)[0]:
+            hdr = 8 if effort == 0 else 16
+            b = bytearray(s)
+            for _ in range(8):  # flip payload bits
+                pos = int(rng.integers(hdr, len(b)))
+                b[pos] ^= 1 << int(rng.integers(0, 8))
+            bad.append(bytes(b))
+            bad.append(s[:hdr] + bytes(rng.integers(0, 256, size=len(s) - hdr, dtype=np.uint8)))  # garbage payload
+            bad.append(s[: hdr + max(1, (len(s) - hdr) // 3)])                                         # truncated
+            bad.append(s[:hdr] + b"\xff" * (len(s) - hdr))
+            bad.append(s[:hdr] + b"\x00" * (len(s) - hdr))
+    out = codec.decode_batch(bad)
+    assert len(out) == len(bad)
+    for d in out:
+        assert d is None or d[0].ndim == 2
+    # the context is still healthy afterwards
+    good = codec.encode_batch(imgs, 0, 1)[0]
+    assert all(np.array_equal(d[0], im) for d, im in zip(codec.decode_batch(good), imgs))
+
+
 def test_context_reuse_and_concurrent_contexts(api, oracle):
     """Scratch buffers grow and are reused across calls of different shapes; two contexts on two host
     threads code at the same time (the reference's functions are re-entrant)."""
