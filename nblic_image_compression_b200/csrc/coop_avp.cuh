@@ -139,11 +139,25 @@ NB_DEV void avp_predict_pair(AvpSmem &sm, const i64 (&E)[AvpGeom<N>::NS], const 
     constexpr int kUnroll = N > 6 ? 1 : N;
 #pragma unroll kUnroll
     for (int k = 0; k + 1 < N; k++) { /* forward elimination with partial pivoting */
-        int piv = k;
-        i64 best = labs64(A[k * N + k]);
-        for (int r = k + 1; r < N; r++) {
-            const i64 m = labs64(A[r * N + k]);
-            if (m > best) { best = m; piv = r; } /* first row of maximal magnitude */
+        /* pivot = first row of maximal magnitude in column k (the order the reference's scan produces) */
+        i64 best;
+        int piv;
+        if constexpr (N > 6) { /* lane hl looks at row k + hl, a 16-lane butterfly keeps (larger magnitude, then smaller row) */
+            best = k + hl < N ? labs64(A[(k + hl) * N + k]) : (i64)0x8000000000000000ull;
+            piv = k + hl < N ? k + hl : 127;
+#pragma unroll
+            for (int m = 8; m >= 1; m >>= 1) {
+                const i64 ov = shfl64_xor(best, m);
+                const int oi = __shfl_xor_sync(0xffffffffu, piv, m);
+                if (ov > best || (ov == best && oi < piv)) { best = ov; piv = oi; }
+            }
+        } else { /* six rows or fewer: every lane scans them (cheaper than four shuffle rounds) */
+            piv = k;
+            best = labs64(A[k * N + k]);
+            for (int r = k + 1; r < N; r++) {
+                const i64 m = labs64(A[r * N + k]);
+                if (m > best) { best = m; piv = r; }
+            }
         }
         __syncwarp();
         if (alive && piv != k) { /* swap rows k and piv: columns k..N-1 and b */
@@ -156,7 +170,8 @@ NB_DEV void avp_predict_pair(AvpSmem &sm, const i64 (&E)[AvpGeom<N>::NS], const 
         if (alive) {
             const Rcp64 rc = make_rcp(d);
             const int W = N - k, cnt = (N - 1 - k) * W; /* per row: columns k+1..N-1, then b */
-            const u32 w_magic = 65536u / (u32)W + 1u;   /* e / W == (e * w_magic) >> 16 for e < 128 */
+            constexpr u32 kWMagic[11] = {0, 65537, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554}; /* 65536 / W + 1 */
+            const u32 w_magic = kWMagic[W];             /* e / W == (e * w_magic) >> 16 for e < 128 */
             for (int e = hl; e < cnt; e += 16) {
                 const int ro = (int)(((u32)e * w_magic) >> 16), cc = e - ro * W, r = k + 1 + ro;
                 const i64 f = A[r * N + k];
