@@ -23,9 +23,10 @@
 
 namespace nblic {
 
-struct QCoopSmem { /* encoder */
-    int ctx[Q_CTX_ENTRIES]; /* 12 KB bias-cancel table                                           */
-    u32 tab[Q_TAB_ENTRIES]; /* 12 KB counts, then freq | cumulative << 16                        */
+struct QCoopSmem { /* encoder: only the bias table is latency critical; the 12 x 256 counters (then freq | cumulative << 16)
+                     * live in global memory / L2 -- pass 1 adds to them with fire-and-forget atomics, pass 2 fetches 32
+                     * symbols' entries one block ahead -- which doubles the resident streams per SM (17 instead of 8) */
+    int ctx[Q_CTX_ENTRIES]; /* 12 KB bias-cancel table */
 };
 enum { Q_CUM_STRIDE = 258 }; /* 257 cumulative frequencies per class (freq = difference), padded to 4 bytes */
 struct QDecSmem { /* decoder: 19.2 KB instead of 25 KB, 11 instead of 8 resident streams per SM */
@@ -58,29 +59,29 @@ NB_DEV void q_serial_row(const uint8_t *img, int w, int i, Smem &sm, int lane, O
 }
 
 /* writes the 12 histogram descriptions; lanes 0..11 work side by side.  Returns the advanced word index. */
-NB_DEV u32 q_finish_histograms(QCoopSmem &sm, uint16_t *out, u32 o, u32 cap, int lane) {
+NB_DEV u32 q_finish_histograms(u32 *tab, uint16_t *out, u32 o, u32 cap, int lane) {
     u32 mine = 0;
     if (lane < Q_CLASSES) {
-        q_normalise(sm.tab + lane * 256);
-        mine = q_put_hist(out, 0, 0, sm.tab + lane * 256); /* dry run: cap 0 suppresses the stores */
+        q_normalise(tab + lane * 256);
+        mine = q_put_hist(out, 0, 0, tab + lane * 256); /* dry run: cap 0 suppresses the stores */
     }
     u32 before = mine; /* exclusive prefix over lanes */
 #pragma unroll
     for (int d = 1; d < 16; d <<= 1) { const u32 t = __shfl_up_sync(FULL, before, d); if (lane >= d) before += t; }
     before -= mine;
     if (lane < Q_CLASSES) {
-        q_put_hist(out + o + before, 0, o + before < cap ? cap - (o + before) : 0, sm.tab + lane * 256);
-        q_pack_cumulative(sm.tab + lane * 256);
+        q_put_hist(out + o + before, 0, o + before < cap ? cap - (o + before) : 0, tab + lane * 256);
+        q_pack_cumulative(tab + lane * 256);
     }
     const u32 total = __shfl_sync(FULL, before + mine, Q_CLASSES - 1);
     __syncwarp();
     return o + total;
 }
 
-__device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u32 cap, uint8_t *sym8, QCoopSmem &sm, int lane, u32 &head_words,
-                              u32 &tail_words) {
+__device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u32 cap, uint8_t *sym8, QCoopSmem &sm, u32 *tab, int lane,
+                              u32 &head_words, u32 &tail_words) {
     uint16_t *sym = reinterpret_cast<uint16_t *>(sym8); /* cls | y << 8 per pixel, raster order */
-    for (int k = lane; k < Q_CTX_ENTRIES; k += 32) { sm.ctx[k] = 0; sm.tab[k] = 0; }
+    for (int k = lane; k < Q_CTX_ENTRIES; k += 32) { sm.ctx[k] = 0; tab[k] = 0; }
     __syncwarp();
 
     for (int i = 0; i < h; i++) { /* pass 1: model every pixel.  R: QNBLIC.c:586-623 */
@@ -89,7 +90,7 @@ __device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u
             q_serial_row<false>(img, w, i, sm, lane, [&](int j, int cls, int px, int sign) {
                 const int x = row[j];
                 const int y = q_fold(x, px, sign);
-                if (lane == 0) { sym[(size_t)i * w + j] = (uint16_t)(cls | (y << 8)); sm.tab[cls * 256 + y]++; }
+                if (lane == 0) { sym[(size_t)i * w + j] = (uint16_t)(cls | (y << 8)); atomicAdd(&tab[cls * 256 + y], 1u); }
                 return x;
             });
             continue;
@@ -127,7 +128,7 @@ __device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u
                 __syncwarp();
             }
             if (active) {
-                atomicAdd(&sm.tab[cls * 256 + y], 1u);
+                atomicAdd(&tab[cls * 256 + y], 1u); /* result unused: a fire-and-forget reduction in L2 */
                 sym[(size_t)i * w + j] = (uint16_t)(cls | (y << 8));
             }
         }
@@ -136,19 +137,27 @@ __device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u
 
     if (cap < 8) return false;
     if (lane == 0) { out[0] = 0x3051; out[1] = 0x322e; out[2] = (uint16_t)h; out[3] = (uint16_t)w; } /* R: QNBLIC.c:463-473 */
-    const u32 o = q_finish_histograms(sm, out, 4, cap, lane);
+    const u32 o = q_finish_histograms(tab, out, 4, cap, lane);
     if (o >= cap) return false;
 
     /* pass 2: rANS, last pixel first, words written downwards from the end of the slot.  R: QNBLIC.c:238-253,635-650 */
     u32 state = 1u << 16, p = cap;
     bool ok = true;
     const long long n = (long long)h * w;
-    for (long long base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
+    auto fetch = [&](long long base, u32 &e, u32 &m) { /* (freq | cumulative << 16, reciprocal) of the block's 32 symbols */
         const long long idx = base + lane;
-        const bool valid = idx < n;
-        const u32 pair = valid ? (u32)sym[idx] : 0u;
-        const u32 e = sm.tab[(pair & 255u) * 256 + (pair >> 8)];
-        const u32 m = 0xffffffffu / max(e & 0xffffu, 1u); /* floor((2^32 - 1) / freq): quotient estimate low by at most 2 */
+        e = 1u; m = 0u;
+        if (base >= 0 && idx < n) {
+            const u32 pair = (u32)sym[idx];
+            e = __ldcg(tab + (pair & 255u) * 256 + (pair >> 8));
+            m = 0xffffffffu / max(e & 0xffffu, 1u); /* floor((2^32 - 1) / freq): quotient estimate low by at most 2 */
+        }
+    };
+    u32 e, m, e_next, m_next;
+    long long base = ((n - 1) / 32) * 32;
+    fetch(base, e, m);
+    for (; base >= 0; base -= 32) {
+        fetch(base - 32, e_next, m_next); /* one block ahead: the L2 latency hides behind the 32 coder steps */
         const int last = (int)min(31ll, n - 1 - base);
         for (int jj = last; jj >= 0; jj--) {
             const u32 ej = __shfl_sync(FULL, e, jj), mj = __shfl_sync(FULL, m, jj);
@@ -165,6 +174,7 @@ __device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u
             }
             state = r + (q << Q_NORM_BITS) + cum;
         }
+        e = e_next; m = m_next;
     }
     if (p >= o + 2) { p -= 2; if (lane == 0) { out[p + 1] = (uint16_t)state; out[p] = (uint16_t)(state >> 16); } } else ok = false;
     head_words = o; tail_words = cap - p;

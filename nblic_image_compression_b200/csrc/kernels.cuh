@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *
 /* Warp-cooperative QNBLIC kernel (coop_qnblic.cuh): one warp per CTA, bias table and the 12 histograms in
  * shared memory. */
 template <bool DEC>
-__global__ void __launch_bounds__(32) coop_q_kernel(Task *tasks, const int *order, int n_order, int *queue) {
+__global__ void __launch_bounds__(32) coop_q_kernel(Task *tasks, const int *order, int n_order, int *queue, u32 *tabs) {
     __shared__ typename std::conditional<DEC, QDecSmem, QCoopSmem>::type sm;
     const int lane = threadIdx.x;
     for (;;) {
@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(32) coop_q_kernel(Task *tasks, const int *orde
         if constexpr (DEC) coop_q_decode(reinterpret_cast<const uint16_t *>(t.slot), t.slot_cap / 2, t.rec, t.h, t.w, sm, lane);
         else {
             u32 head = 0, tail = 0;
-            const bool ok = coop_q_encode(t.src, t.h, t.w, reinterpret_cast<uint16_t *>(t.slot), t.slot_cap / 2, t.sym, sm, lane, head, tail);
+            const bool ok = coop_q_encode(t.src, t.h, t.w, reinterpret_cast<uint16_t *>(t.slot), t.slot_cap / 2, t.sym, sm,
+                                          tabs + (size_t)blockIdx.x * Q_TAB_ENTRIES, lane, head, tail);
             if (lane == 0) {
                 if (ok) { t.head_len = head * 2; t.tail_len = tail * 2; }
                 else { t.status = NBLIC_B200_OVERFLOW; t.head_len = t.tail_len = 0; }

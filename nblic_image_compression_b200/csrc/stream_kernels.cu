@@ -134,7 +134,8 @@ int launch_coop_q(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_que
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_q_kernel<DEC>, 32, 0));
     const int grid = std::min(n_order, c->sm_count * std::max(per_sm, 1));
-    coop_q_kernel<DEC><<<grid, 32, 0, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue);
+    if (!DEC) CK(c->coop_counts.reserve((size_t)grid * Q_TAB_ENTRIES * sizeof(u32))); /* encoder: per-CTA symbol statistics in L2 */
+    coop_q_kernel<DEC><<<grid, 32, 0, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (u32 *)c->coop_counts.p);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
