@@ -31,6 +31,17 @@ def test_header_symbols_exported(lib):
         assert getattr(lib, sym) is not None
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/nblic_b200.h must be consumable by a C99 compiler (the reference and its CLI are C)."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "nblic_b200.h"\n'
+                   "int probe(void) { int (*f)(int, unsigned char *, unsigned char *, int, int, int *, int *) = NBLICcompress;\n"
+                   "  size_t (*g)(int, int) = nblic_b200_stream_bound; return f != 0 && g != 0 && NBLIC_MAX_IMG_SIZE == 100000000; }\n")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                    "-o", str(tmp_path / "use_header.o")], check=True)
+
+
 def test_peek_and_bound(lib):
     from nblic_image_compression_b200 import api
     from conftest import GOLDEN
