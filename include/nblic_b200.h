@@ -44,8 +44,9 @@ int NBLICcompress(int verbose, unsigned char *p_buf, unsigned char *p_img, int h
                   int *p_near, int *p_effort);
 
 /* src/NBLIC.h:72.  Returns 0 / -1; writes height, width, near and effort parsed from the header.
- * The reference ABI carries no stream length: the wrapper uploads nblic_b200_stream_bound(h, w)
- * bytes starting at p_buf unless nblic_b200_hint_input_len() was called (see below). */
+ * The reference ABI carries no stream length: unless nblic_b200_hint_input_len() was called (see below) the
+ * wrapper takes min(nblic_b200_stream_bound(h, w), readable extent of p_buf) bytes -- it probes, and never
+ * faults on, the end of the caller's mapping, so an exact-size buffer is fine. */
 int NBLICdecompress(int verbose, unsigned char *p_buf, unsigned char *p_img, int *p_height, int *p_width,
                     int *p_near, int *p_effort);
 
@@ -57,8 +58,8 @@ int QNBLICcompress(uint16_t *p_buf, unsigned char *p_img, int height, int width)
 int QNBLICcompressMultiThread(uint16_t *p_buf, unsigned char *p_img, int height, int width);
 
 /* Optional side channel for the two legacy decompress calls: number of valid bytes at p_buf for the
- * NEXT decompress call on this thread (reset after use).  Without it the wrappers read
- * min(nblic_b200_stream_bound(h, w), 200 MB) bytes, which is safe behind src/NBLIC_main.c:141's static buffer. */
+ * NEXT decompress call on this thread (reset after use).  Without it the wrappers copy
+ * min(nblic_b200_stream_bound(h, w), 200 MB, readable extent) bytes through a fault-safe bounce buffer. */
 void nblic_b200_hint_input_len(size_t n_bytes);
 
 /* Worst-case stream size in bytes for an h x w image (any effort / near); what callers should
@@ -132,13 +133,20 @@ int nblic_b200_encode_batch_device(nblic_b200_ctx *ctx, int n, const uint8_t *d_
                                    const int *heights, const int *widths, int near, int effort,
                                    uint8_t *d_streams, uint64_t stream_cap, uint64_t *stream_off,
                                    uint8_t *d_recon, int *status);
+/* pix_cap[i] = bytes reserved for raster i at d_pixels + pix_off[i] (host array, n entries).  The raster size comes
+ * from the stream header in device memory, so a stream whose height x width exceeds pix_cap[i] is reported
+ * NBLIC_B200_OVERFLOW and not decoded.  NULL disables the check (trusted streams only). */
 int nblic_b200_decode_batch_device(nblic_b200_ctx *ctx, int n, const uint8_t *d_streams, const uint64_t *stream_off,
-                                   uint8_t *d_pixels, const uint64_t *pix_off, int *status);
+                                   uint8_t *d_pixels, const uint64_t *pix_off, const uint64_t *pix_cap, int *status);
 
 /* Deterministic synthetic gray image written to device memory; occluders is
  * the 12 x 5 int32 table {cx, cy, rad, off, kind} (nblic_image_compression_b200/synth.py). */
 int nblic_b200_synth_gray(nblic_b200_ctx *ctx, uint8_t *d_out, int height, int width, uint32_t seed,
                           const int32_t *occluders);
+
+/* n equal-size images, seeds seed0 + k * seed_stride, packed back to back at d_out; occluders = n tables of 12 x 5 int32. */
+int nblic_b200_synth_gray_batch(nblic_b200_ctx *ctx, uint8_t *d_out, int n, int height, int width, uint32_t seed0,
+                                uint32_t seed_stride, const int32_t *occluders);
 
 /* Test hook: out[i] = trunc(num[i] / den[i]) computed by the kernels' reciprocal-based exact 64-bit
  * division (csrc/coop_avp.cuh: div_rcp); den[i] == 0 yields 0.  Host arrays. */
@@ -148,6 +156,8 @@ int nblic_b200_debug_divcheck(nblic_b200_ctx *ctx, const int64_t *num, const int
  * duration (ms, on ctx's stream) of the coder kernel of the most recent batch call. */
 uint64_t nblic_b200_launch_count(const nblic_b200_ctx *ctx);
 float nblic_b200_last_coder_ms(const nblic_b200_ctx *ctx);
+/* coder streams the most recent cooperative launch could hold resident at once (fill = streams / slots) */
+int nblic_b200_last_slots(const nblic_b200_ctx *ctx);
 /* The CUDA stream (cudaStream_t) every call of this context issues its work on, for callers that
  * want to bracket calls with their own CUDA events. */
 void *nblic_b200_stream_handle(const nblic_b200_ctx *ctx);

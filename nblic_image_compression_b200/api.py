@@ -30,8 +30,8 @@ SYMBOLS = [
     # batch layer
     "nblic_b200_create", "nblic_b200_destroy", "nblic_b200_last_error", "nblic_b200_set_mapping",
     "nblic_b200_encode_batch", "nblic_b200_decode_batch", "nblic_b200_peek",
-    "nblic_b200_encode_batch_device", "nblic_b200_decode_batch_device", "nblic_b200_synth_gray", "nblic_b200_debug_divcheck",
-    "nblic_b200_launch_count", "nblic_b200_last_coder_ms", "nblic_b200_last_mapping", "nblic_b200_stream_handle", "nblic_b200_version",
+    "nblic_b200_encode_batch_device", "nblic_b200_decode_batch_device", "nblic_b200_synth_gray", "nblic_b200_synth_gray_batch", "nblic_b200_debug_divcheck",
+    "nblic_b200_launch_count", "nblic_b200_last_coder_ms", "nblic_b200_last_slots", "nblic_b200_last_mapping", "nblic_b200_stream_handle", "nblic_b200_version",
 ]
 
 _lib = None
@@ -60,8 +60,10 @@ def load_library() -> C.CDLL:
     lib.nblic_b200_peek.argtypes = [C.c_void_p, C.c_size_t, _ip, _ip, _ip, _ip]
     lib.nblic_b200_encode_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, _u64p, _ip, _ip, C.c_int, C.c_int,
                                                    C.c_void_p, C.c_uint64, _u64p, C.c_void_p, _ip]
-    lib.nblic_b200_decode_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, _u64p, C.c_void_p, _u64p, _ip]
+    lib.nblic_b200_decode_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, _u64p, C.c_void_p, _u64p, _u64p, _ip]
     lib.nblic_b200_synth_gray.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int32)]
+    lib.nblic_b200_synth_gray_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]
+    lib.nblic_b200_last_slots.argtypes = [C.c_void_p]
     lib.nblic_b200_debug_divcheck.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.nblic_b200_launch_count.restype = C.c_uint64
     lib.nblic_b200_launch_count.argtypes = [C.c_void_p]
@@ -164,19 +166,21 @@ class Codec:
         streams = [outs[i][: lens[i]].tobytes() if status[i] == OK else None for i in range(n)]
         return streams, recs, [status[i] for i in range(n)]
 
-    def decode_batch(self, streams: Sequence[bytes]):
-        """-> list of (img, near, effort) or None per stream"""
+    def decode_batch(self, streams: Sequence[bytes], img_caps: Optional[Sequence[Optional[int]]] = None):
+        """-> list of (img, near, effort) or None per stream; the per-stream result codes stay in self.last_status.
+        img_caps[i] (optional) overrides the capacity reported for raster i (to exercise NBLIC_B200_OVERFLOW)."""
         n = len(streams)
         bufs = [np.frombuffer(s, dtype=np.uint8) if len(s) else np.zeros(1, np.uint8) for s in streams]
         lens = (C.c_size_t * max(n, 1))(*[len(s) for s in streams])
         heads = [peek(bytes(s[:16])) for s in streams]
         imgs = [np.empty(max(h[0] * h[1], 1) if h else 1, dtype=np.uint8) for h in heads]
-        caps = (C.c_size_t * max(n, 1))(*[a.size for a in imgs])
+        caps = (C.c_size_t * max(n, 1))(*[a.size if not img_caps or img_caps[i] is None else img_caps[i] for i, a in enumerate(imgs)])
         hs, ws, ns, es, status = ((C.c_int * max(n, 1))() for _ in range(5))
         rc = self.lib.nblic_b200_decode_batch(self.ctx, n, _ptr_array(bufs), lens, _ptr_array(imgs), caps, hs, ws, ns, es, status)
         if rc < 0:
             raise RuntimeError("nblic_b200_decode_batch: " + self._err())
         out = []
+        self.last_status = [status[i] for i in range(n)]
         for i in range(n):
             if status[i] != OK:
                 out.append(None)
@@ -201,13 +205,18 @@ class Codec:
             raise RuntimeError("nblic_b200_encode_batch_device: " + self._err())
         return stream_off, status[:n], rc
 
-    def decode_device(self, d_streams: int, stream_off: np.ndarray, d_pixels: int, pix_off: np.ndarray):
+    def decode_device(self, d_streams: int, stream_off: np.ndarray, d_pixels: int, pix_off: np.ndarray, pix_cap: Optional[np.ndarray] = None):
+        """pix_cap[i] = bytes reserved for raster i (None: unchecked, trusted streams only) -> (status int32[n], rc)"""
         n = len(pix_off)
         stream_off = np.ascontiguousarray(stream_off, dtype=np.uint64)
         pix_off = np.ascontiguousarray(pix_off, dtype=np.uint64)
+        if pix_cap is not None:
+            pix_cap = np.ascontiguousarray(pix_cap, dtype=np.uint64)
         status = np.zeros(max(n, 1), dtype=np.int32)
         rc = self.lib.nblic_b200_decode_batch_device(self.ctx, n, d_streams, stream_off.ctypes.data_as(_u64p), d_pixels,
-                                                     pix_off.ctypes.data_as(_u64p), status.ctypes.data_as(_ip))
+                                                     pix_off.ctypes.data_as(_u64p),
+                                                     pix_cap.ctypes.data_as(_u64p) if pix_cap is not None else None,
+                                                     status.ctypes.data_as(_ip))
         if rc < 0:
             raise RuntimeError("nblic_b200_decode_batch_device: " + self._err())
         return status[:n], rc
@@ -226,6 +235,20 @@ class Codec:
         rc = self.lib.nblic_b200_synth_gray(self.ctx, d_out, h, w, seed & 0xFFFFFFFF, occ.ctypes.data_as(C.POINTER(C.c_int32)))
         if rc != 0:
             raise RuntimeError("nblic_b200_synth_gray: " + self._err())
+
+
+    def synth_device_batch(self, d_out: int, n: int, h: int, w: int, seed0: int, seed_stride: int = 1):
+        """n images of h x w, seeds seed0 + k * seed_stride, packed back to back at d_out (one launch per 32768 images)"""
+        from .synth import occluders
+        occ = np.ascontiguousarray(np.stack([occluders(h, w, seed0 + i * seed_stride) for i in range(n)]), dtype=np.int32)
+        rc = self.lib.nblic_b200_synth_gray_batch(self.ctx, d_out, n, h, w, seed0 & 0xFFFFFFFF, seed_stride & 0xFFFFFFFF,
+                                                  occ.ctypes.data_as(C.POINTER(C.c_int32)))
+        if rc != 0:
+            raise RuntimeError("nblic_b200_synth_gray_batch: " + self._err())
+
+    @property
+    def last_slots(self) -> int:
+        return int(self.lib.nblic_b200_last_slots(self.ctx))
 
 
 class legacy:

@@ -60,5 +60,27 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def source_fingerprint() -> str:
+    """16 hex digits over the kernel sources and compile flags: stamps ncu captures so that bench.py only quotes
+    profile figures taken from the code it is running (the GPU box has no .git to ask for HEAD)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for name in sorted(os.listdir(CSRC)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(name.encode())
+            h.update(open(os.path.join(CSRC, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def build_microbench() -> str:
+    """tools/microbench/int_issue_peak: the integer-issue peak measurement the roofline is quoted against."""
+    src = os.path.join(HERE, "..", "tools", "microbench", "int_issue_peak.cu")
+    out = os.path.join(HERE, "..", "tools", "microbench", "int_issue_peak")
+    if _stale(out, [src]):
+        subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-o", out, src], check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_microbench())

@@ -290,8 +290,11 @@ __device__ __forceinline__ int lattice(u32 key, int ix, int iy) { return (int)(h
 
 struct Occluders { int v[12][5]; };
 
-__global__ void __launch_bounds__(256) synth_gray_kernel(uint8_t *out, int h, int w, u32 seed, Occluders occ) {
+/* one image (gridDim.y == 1, occluders by value) or a batch of equal-size images (blockIdx.y = image, seed + blockIdx.y * seed_stride,
+ * occluder tables in `occ_batch`, rasters packed back to back) */
+__global__ void __launch_bounds__(256) synth_gray_kernel(uint8_t *out, int h, int w, u32 seed, u32 seed_stride, Occluders occ, const Occluders *occ_batch) {
     const long long n = (long long)h * w;
+    if (occ_batch) { occ = occ_batch[blockIdx.y]; seed += blockIdx.y * seed_stride; out += (size_t)blockIdx.y * (size_t)n; }
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
         const int y = (int)(p / w), x = (int)(p % w);
         const int shifts[7] = {8, 7, 6, 5, 4, 3, 2}, amps[7] = {64, 48, 32, 20, 12, 7, 4};

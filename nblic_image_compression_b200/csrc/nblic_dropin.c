@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "../../include/nblic_b200.h"
 
@@ -64,12 +65,44 @@ int NBLICcompress(int verbose, unsigned char *p_buf, unsigned char *p_img, int h
     return len;
 }
 
-static size_t legacy_input_len(int h, int w) {
-    size_t n = g_hint_len;
-    g_hint_len = 0;
-    if (n) return n;
-    n = nblic_b200_stream_bound(h, w);
-    return n < (size_t)2 * NBLIC_MAX_IMG_SIZE ? n : (size_t)2 * NBLIC_MAX_IMG_SIZE; /* src/NBLIC_main.c:141 */
+/*
+ * The reference decoders get no input length (src/NBLIC.h:72, src/QNBLIC.h:14): they read forward until the last
+ * pixel is out.  A GPU decoder has to upload the stream first, so the legacy wrappers need an extent.  With the
+ * side-channel hint that is the caller's figure.  Without it the wrappers take the worst-case stream size for the
+ * parsed dimensions, but never touch memory the caller does not own: the bytes are copied through a pipe
+ * (write(2) from the caller's buffer, read(2) into a bounce buffer), and the kernel stops a write at the first
+ * unreadable page instead of faulting.  The copy therefore ends at min(worst case, readable extent); whatever lies
+ * between the true end of the stream and that point is uploaded and never looked at (a valid stream is consumed
+ * exactly to its end).
+ */
+static uint8_t *readable_prefix(const uint8_t *src, size_t want, size_t *got) {
+    int fd[2];
+    uint8_t *bounce = (uint8_t *)malloc(want ? want : 1);
+    size_t done = 0;
+    *got = 0;
+    if (!bounce) return NULL;
+    if (pipe(fd) != 0) { free(bounce); return NULL; }
+    while (done < want) {
+        /* pieces stay below the default pipe capacity (write never blocks) and, after a head piece that ends at a page
+         * boundary of the source, start page-aligned: the kernel copies pipe pages whole and drops a partly copied one,
+         * so only an aligned piece is guaranteed to deliver every readable byte in front of a protected page */
+        const size_t to_page = 4096 - (size_t)((uintptr_t)(src + done) & 4095);
+        size_t piece = to_page < 4096 ? to_page : 32768;
+        ssize_t wr, rd = 0;
+        if (piece > want - done) piece = want - done;
+        wr = write(fd[1], src + done, piece);
+        if (wr <= 0) break; /* EFAULT: the first byte of the piece is already unreadable */
+        while (rd < wr) {
+            ssize_t r = read(fd[0], bounce + done + rd, (size_t)(wr - rd));
+            if (r <= 0) break;
+            rd += r;
+        }
+        done += (size_t)rd;
+        if ((size_t)wr < piece || rd < wr) break; /* short write: the piece ran into an unreadable page */
+    }
+    close(fd[0]); close(fd[1]);
+    *got = done;
+    return bounce;
 }
 
 static int decode_one(const uint8_t *stream, size_t len, unsigned char *p_img, int h, int w) {
@@ -82,13 +115,29 @@ static int decode_one(const uint8_t *stream, size_t len, unsigned char *p_img, i
     return rc == 0 ? 0 : -1;
 }
 
+/* decode p_buf with the extent rules above */
+static int decode_legacy(const uint8_t *p_buf, unsigned char *p_img, int h, int w) {
+    size_t n = g_hint_len, got = 0;
+    uint8_t *bounce;
+    int rc;
+    g_hint_len = 0;
+    if (n) return decode_one(p_buf, n, p_img, h, w);
+    n = nblic_b200_stream_bound(h, w);
+    if (n > (size_t)2 * NBLIC_MAX_IMG_SIZE) n = (size_t)2 * NBLIC_MAX_IMG_SIZE; /* src/NBLIC_main.c:141 */
+    bounce = readable_prefix(p_buf, n, &got);
+    if (!bounce) return -1;
+    rc = got ? decode_one(bounce, got, p_img, h, w) : -1;
+    free(bounce);
+    return rc;
+}
+
 int NBLICdecompress(int verbose, unsigned char *p_buf, unsigned char *p_img, int *p_height, int *p_width, int *p_near, int *p_effort) {
     int h = 0, w = 0, near = 0, effort = 0, rc;
     if (memcmp(p_buf, "NBLIC0.3", 8) != 0) return -1; /* src/NBLIC.c:700-702: nothing is written on a bad magic */
     rc = nblic_b200_peek(p_buf, 16, &h, &w, &near, &effort);
     *p_height = h; *p_width = w; *p_near = near; *p_effort = effort; /* src/NBLIC.c:703-711 */
     if (rc != 0) return -1;
-    rc = decode_one(p_buf, legacy_input_len(h, w), p_img, h, w);
+    rc = decode_legacy(p_buf, p_img, h, w);
     if (verbose && rc == 0) printf("\r    %d rows (B200)\n", h);
     return rc;
 }
@@ -112,5 +161,5 @@ int QNBLICdecompress(uint16_t *p_buf, unsigned char *p_img, int *p_height, int *
     rc = nblic_b200_peek(bytes, 8, &h, &w, &near, &effort);
     *p_height = h; *p_width = w;
     if (rc != 0) return -1;
-    return decode_one(bytes, legacy_input_len(h, w), p_img, h, w);
+    return decode_legacy(bytes, p_img, h, w);
 }

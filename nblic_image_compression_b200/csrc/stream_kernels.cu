@@ -82,6 +82,15 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct LaunchPlan { int map; int grid; size_t cold_stride; size_t smem; };
 
+/* Persistent grid for n queued streams when `slots` can be resident: the number of waves is fixed by the residency,
+ * but spreading the streams evenly over the waves (10 000 streams, 3 108 slots: 4 waves of 2 500 instead of 3 full
+ * ones and a 22 % tail) leaves fewer streams competing for the issue slots of an SM in every wave. */
+int balanced_grid(int n, int slots) {
+    if (n <= slots) return std::max(n, 1);
+    const int waves = (n + slots - 1) / slots;
+    return (n + waves - 1) / waves;
+}
+
 template <int KIND, bool DEC, int MAP>
 int launch_coder_t(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, const LaunchPlan &plan, size_t avp_stride) {
     auto kern = coder_kernel<KIND, DEC, MAP>;
@@ -133,7 +142,7 @@ template <bool DEC>
 int launch_coop_q(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue) {
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_q_kernel<DEC>, 32, 0));
-    const int grid = std::min(n_order, c->sm_count * std::max(per_sm, 1));
+    const int grid = balanced_grid(n_order, c->sm_count * std::max(per_sm, 1));
     if (!DEC) CK(c->coop_counts.reserve((size_t)grid * Q_TAB_ENTRIES * sizeof(u32))); /* encoder: per-CTA symbol statistics in L2 */
     coop_q_kernel<DEC><<<grid, 32, 0, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (u32 *)c->coop_counts.p);
     c->launches++;
@@ -151,7 +160,7 @@ int launch_coop_t(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_que
     const int slots = c->sm_count * std::max(per_sm, 1);
     if (slots_out) *slots_out = slots;
     if (probe_only) return 0;
-    int grid = std::min(n_order, slots);
+    int grid = balanced_grid(n_order, slots);
     size_t avp_half = 0;
     if (NAVP > 0) { /* B and F: one m-vector per image column each; bound the grid by a 32 GB budget */
         avp_half = (size_t)max_w * (1 + NAVP + NAVP * NAVP);
@@ -318,6 +327,7 @@ int nblic_b200_set_mapping(nblic_b200_ctx *c, int mapping) {
 uint64_t nblic_b200_launch_count(const nblic_b200_ctx *c) { return c ? c->launches : 0; }
 float nblic_b200_last_coder_ms(const nblic_b200_ctx *c) { return c ? c->coder_ms : 0.f; }
 const char *nblic_b200_last_mapping(const nblic_b200_ctx *c) { return c ? c->last_map : "none"; }
+int nblic_b200_last_slots(const nblic_b200_ctx *c) { return c ? c->last_slots : 0; }
 void *nblic_b200_stream_handle(const nblic_b200_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 int nblic_b200_peek(const uint8_t *stream, size_t len, int *height, int *width, int *near, int *effort) {
@@ -383,7 +393,7 @@ int nblic_b200_encode_batch_device(nblic_b200_ctx *c, int n, const uint8_t *d_pi
     u32 max_cap = 0;
     for (const Task &t : tasks) max_cap = std::max(max_cap, t.slot_cap);
     const u32 chunk = 16384;
-    dim3 grid((max_cap + chunk - 1) / chunk, (unsigned)n);
+    dim3 grid((unsigned)n, (max_cap + chunk - 1) / chunk); /* image index on x (2^31-1 blocks), piece index on y (<= 200 MB / 16 KB) */
     gather_streams_kernel<<<grid, 256, 0, c->stream>>>((const Task *)c->tasks.p, (const unsigned long long *)c->offsets.p, d_streams,
                                                         stream_cap, chunk, (int *)c->flags.p);
     c->launches++;
@@ -404,7 +414,7 @@ int nblic_b200_encode_batch_device(nblic_b200_ctx *c, int n, const uint8_t *d_pi
 
 /* starts[i], lens[i]: extent of stream i inside d_streams */
 int decode_device_impl(nblic_b200_ctx *c, int n, const uint8_t *d_streams, const uint64_t *starts, const uint64_t *lens,
-                              uint8_t *d_pixels, const uint64_t *pix_off, int *status) {
+                              uint8_t *d_pixels, const uint64_t *pix_off, const uint64_t *pix_cap, int *status) {
     /* header fields of every stream, gathered on the device */
     CK(c->offsets.reserve(sizeof(unsigned long long) * 2 * (size_t)n));
     CK(c->peeks.reserve(sizeof(Peek) * (size_t)n));
@@ -428,6 +438,8 @@ int decode_device_impl(nblic_b200_ctx *c, int n, const uint8_t *d_streams, const
         t.slot_cap = (u32)std::min<uint64_t>(lens[i], 0xfffffff0u);
         t.rec = d_pixels + pix_off[i];
         if (p.ok && p.effort == 0 && ((uintptr_t)t.slot & 1)) t.status = NBLIC_B200_BAD_HEADER; /* QNBLIC words must be 2-byte aligned */
+        /* the raster size comes from the stream itself: never write more than the caller reserved */
+        if (p.ok && pix_cap && (uint64_t)p.h * (uint64_t)p.w > pix_cap[i]) t.status = NBLIC_B200_OVERFLOW;
     }
     if (run_tasks<true>(c, tasks)) return -1;
     if (finish_tasks(c, tasks)) return -1;
@@ -437,14 +449,14 @@ int decode_device_impl(nblic_b200_ctx *c, int n, const uint8_t *d_streams, const
 }
 
 int nblic_b200_decode_batch_device(nblic_b200_ctx *c, int n, const uint8_t *d_streams, const uint64_t *stream_off, uint8_t *d_pixels,
-                                   const uint64_t *pix_off, int *status) {
+                                   const uint64_t *pix_off, const uint64_t *pix_cap, int *status) {
     if (!c) return -1;
     if (n < 0 || (n > 0 && (!d_streams || !stream_off || !d_pixels || !pix_off))) { fail(c, "bad arguments"); return -1; }
     CK(cudaSetDevice(c->device));
     if (n == 0) return 0;
     std::vector<uint64_t> lens((size_t)n);
     for (int i = 0; i < n; i++) lens[(size_t)i] = stream_off[i + 1] - stream_off[i];
-    return decode_device_impl(c, n, d_streams, stream_off, lens.data(), d_pixels, pix_off, status);
+    return decode_device_impl(c, n, d_streams, stream_off, lens.data(), d_pixels, pix_off, pix_cap, status);
 }
 
 int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *images, const int *heights, const int *widths, int near,
@@ -495,20 +507,20 @@ int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *imag
         CK(cudaEventRecord(c->ev_copy[k & 1], c->copy));
         return 0;
     };
-    if (upload(0)) return -1;
+    if (upload(0)) { cudaStreamSynchronize(c->copy); return -1; }
     int failed = 0;
     size_t packed_base = 0; /* chunk k's packed streams start here inside c->streams */
     float coder_ms = 0.f;
     for (int k = 0; k < n_chunks; k++) {
         const int lo = k * chunk_n, hi = std::min(n, lo + chunk_n), cnt = hi - lo;
-        if (k + 1 < n_chunks && upload(k + 1)) return -1;
+        if (k + 1 < n_chunks && upload(k + 1)) { cudaStreamSynchronize(c->copy); return -1; }
         CK(cudaStreamWaitEvent(c->stream, c->ev_copy[k & 1], 0));
         size_t bound_k = 0;
         for (int i = lo; i < hi; i++) if (dims_fine(i)) bound_k += nblic_b200_stream_bound(heights[i], widths[i]);
         uint8_t *d_packed = (uint8_t *)c->streams.p + packed_base;
         int rc = nblic_b200_encode_batch_device(c, cnt, d_pix, pix_off.data() + lo, heights + lo, widths + lo, near, effort, d_packed,
                                                 std::max<size_t>(bound_k, 16), stream_off.data(), d_rec, st.data() + lo);
-        if (rc < 0) return -1;
+        if (rc < 0) { cudaStreamSynchronize(c->copy); return -1; }
         coder_ms += c->coder_ms;
         for (int i = lo; i < hi; i++) { /* the device call has completed: downloads go to the copy stream */
             out_lens[i] = 0;
@@ -541,7 +553,7 @@ int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *stre
     std::vector<uint64_t> pix_off((size_t)n), stream_off((size_t)n + 1);
     std::vector<int> st((size_t)n, NBLIC_B200_OK);
     std::vector<Peek> peeks((size_t)n);
-    std::vector<uint64_t> lens((size_t)n);
+    std::vector<uint64_t> lens((size_t)n), pix_cap((size_t)n);
     size_t pix_total = 0, stream_total = 0;
     for (int i = 0; i < n; i++) {
         Peek p = streams[i] ? peek_bytes(streams[i], stream_lens[i]) : Peek{0, 0, 0, 0, 0, 0};
@@ -554,8 +566,12 @@ int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *stre
         if (efforts) efforts[i] = p.effort;
         pix_off[(size_t)i] = pix_total;
         stream_off[(size_t)i] = stream_total;
-        /* a stream that fails the header check still occupies a 16-byte stub so the device sees the same verdict */
-        lens[(size_t)i] = p.ok ? (uint64_t)stream_lens[i] : (uint64_t)std::min<size_t>(streams[i] ? stream_lens[i] : 0, 16);
+        /* a stream that fails the header check still occupies a 16-byte stub so the device sees the same verdict; one
+         * whose raster does not fit img_caps[i] gets no bytes at all: its (valid) header must not reach the device, where
+         * no room was reserved for its pixels */
+        lens[(size_t)i] = p.ok ? (uint64_t)stream_lens[i]
+                               : (st[(size_t)i] == NBLIC_B200_OVERFLOW ? 0 : (uint64_t)std::min<size_t>(streams[i] ? stream_lens[i] : 0, 16));
+        pix_cap[(size_t)i] = p.ok ? (uint64_t)p.h * (uint64_t)p.w : 0;
         if (p.ok) pix_total += align_up((size_t)p.h * p.w, 256);
         stream_total += align_up(lens[(size_t)i], 16);
     }
@@ -571,17 +587,17 @@ int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *stre
         CK(cudaEventRecord(c->ev_copy[k & 1], c->copy));
         return 0;
     };
-    if (upload(0)) return -1;
+    if (upload(0)) { cudaStreamSynchronize(c->copy); return -1; }
     std::vector<int> dev_st((size_t)n, NBLIC_B200_OK);
     int failed = 0;
     float coder_ms = 0.f;
     for (int k = 0; k < n_chunks; k++) {
         const int lo = k * chunk_n, hi = std::min(n, lo + chunk_n);
-        if (k + 1 < n_chunks && upload(k + 1)) return -1;
+        if (k + 1 < n_chunks && upload(k + 1)) { cudaStreamSynchronize(c->copy); return -1; }
         CK(cudaStreamWaitEvent(c->stream, c->ev_copy[k & 1], 0));
         int rc = decode_device_impl(c, hi - lo, (const uint8_t *)c->streams.p, stream_off.data() + lo, lens.data() + lo, (uint8_t *)c->pixels.p,
-                                    pix_off.data() + lo, dev_st.data() + lo);
-        if (rc < 0) return -1;
+                                    pix_off.data() + lo, pix_cap.data() + lo, dev_st.data() + lo);
+        if (rc < 0) { cudaStreamSynchronize(c->copy); return -1; }
         coder_ms += c->coder_ms;
         for (int i = lo; i < hi; i++) {
             if (st[(size_t)i] == NBLIC_B200_OK) st[(size_t)i] = dev_st[(size_t)i];
@@ -628,8 +644,33 @@ int nblic_b200_synth_gray(nblic_b200_ctx *c, uint8_t *d_out, int height, int wid
     for (int k = 0; k < 12; k++) for (int f = 0; f < 5; f++) occ.v[k][f] = occluders[k * 5 + f];
     const long long n = (long long)height * width;
     const int grid = (int)std::min<long long>((n + 255) / 256, (long long)c->sm_count * 16);
-    synth_gray_kernel<<<grid, 256, 0, c->stream>>>(d_out, height, width, seed, occ);
+    synth_gray_kernel<<<grid, 256, 0, c->stream>>>(d_out, height, width, seed, 0u, occ, nullptr);
     c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int nblic_b200_synth_gray_batch(nblic_b200_ctx *c, uint8_t *d_out, int n, int height, int width, uint32_t seed0, uint32_t seed_stride,
+                                const int32_t *occluders) {
+    if (!c) return -1;
+    if (n < 0 || (n > 0 && (!d_out || !occluders)) || height <= 0 || width <= 0) { fail(c, "bad arguments"); return -1; }
+    if (n == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    static_assert(sizeof(Occluders) == 60 * sizeof(int32_t), "occluder table layout");
+    CK(c->sym.reserve(sizeof(Occluders) * (size_t)n));
+    CK(cudaMemcpyAsync(c->sym.p, occluders, sizeof(Occluders) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    const long long px = (long long)height * width;
+    const int gx = (int)std::min<long long>((px + 255) / 256, 64);
+    Occluders none;
+    memset(&none, 0, sizeof none);
+    for (int at = 0; at < n; at += 32768) { /* gridDim.y <= 65535 */
+        const int cnt = std::min(n - at, 32768);
+        synth_gray_kernel<<<dim3((unsigned)gx, (unsigned)cnt), 256, 0, c->stream>>>(d_out + (size_t)at * (size_t)px, height, width,
+                                                                                   seed0 + (uint32_t)at * seed_stride, seed_stride, none,
+                                                                                   (const Occluders *)c->sym.p + at);
+        c->launches++;
+    }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     return 0;

@@ -430,3 +430,123 @@ def test_lane_mapping_large_batch_matches_warp(api, codec):
     for im, d in zip(imgs, codec.decode_batch(b)):
         assert np.array_equal(d[0], im)
     codec.set_mapping(api.MAP_AUTO)
+
+
+def test_decode_overflow_leaves_the_neighbours_alone(api, codec):
+    """A stream whose raster exceeds img_caps[i] is reported OVERFLOW and is not decoded (its header is valid, so the
+    device must never see it); the streams next to it in the same chunk decode bit-exact."""
+    imgs = [gen(40, 56, 1), gen(64, 64, 2), gen(24, 31, 3)]
+    for effort, near in [(0, 0), (1, 0), (2, 1)]:
+        streams = codec.encode_batch(imgs, near, effort)[0]
+        full = codec.decode_batch(streams)
+        out = codec.decode_batch(streams, img_caps=[None, 100, None])
+        assert out[1] is None and codec.last_status == [api.OK, api.OVERFLOW, api.OK]
+        assert np.array_equal(out[0][0], full[0][0]) and np.array_equal(out[2][0], full[2][0])
+
+
+def test_decode_device_respects_pix_cap(api, codec):
+    """nblic_b200_decode_batch_device takes the raster size from the stream header in device memory: pix_cap bounds it."""
+    import torch
+    imgs = [gen(32, 48, 5), gen(32, 48, 6), gen(32, 48, 7)]
+    npx = 32 * 48
+    d_pix = torch.from_numpy(np.concatenate([im.ravel() for im in imgs])).to("cuda:0")
+    off = np.arange(3, dtype=np.uint64) * npx
+    hs, ws = np.full(3, 32, np.int32), np.full(3, 48, np.int32)
+    cap = 3 * api.stream_bound(32, 48)
+    d_str = torch.empty(cap, dtype=torch.uint8, device="cuda:0")
+    for effort in (0, 1):
+        so, st, rc = codec.encode_device(d_pix.data_ptr(), off, hs, ws, 0, effort, d_str.data_ptr(), cap)
+        assert rc == 0
+        d_dec = torch.full((3 * npx,), 0xAB, dtype=torch.uint8, device="cuda:0")
+        st, rc = codec.decode_device(d_str.data_ptr(), so, d_dec.data_ptr(), off, pix_cap=np.array([npx, npx - 1, npx], np.uint64))
+        assert rc == 1 and st.tolist() == [api.OK, api.OVERFLOW, api.OK]
+        got = d_dec.cpu().numpy()
+        assert np.array_equal(got[:npx], imgs[0].ravel()) and np.array_equal(got[2 * npx:], imgs[2].ravel())
+        assert (got[npx:2 * npx] == 0xAB).all()  # untouched
+        st, rc = codec.decode_device(d_str.data_ptr(), so, d_dec.data_ptr(), off, pix_cap=np.full(3, npx, np.uint64))
+        assert rc == 0 and np.array_equal(d_dec.cpu().numpy(), d_pix.cpu().numpy())
+
+
+def test_device_batch_beyond_65535_images(api, codec):
+    """The stream gather puts the image index on gridDim.x: batches larger than the gridDim.y limit work."""
+    import torch
+    n, h, w = 70000, 3, 5
+    rng = np.random.default_rng(3)
+    pix = rng.integers(0, 256, size=n * h * w, dtype=np.uint8)
+    d_pix = torch.from_numpy(pix).to("cuda:0")
+    off = np.arange(n, dtype=np.uint64) * (h * w)
+    hs, ws = np.full(n, h, np.int32), np.full(n, w, np.int32)
+    cap = n * api.stream_bound(h, w)
+    d_str = torch.empty(cap, dtype=torch.uint8, device="cuda:0")
+    d_dec = torch.empty(n * h * w, dtype=torch.uint8, device="cuda:0")
+    for effort in (0, 1):
+        so, st, rc = codec.encode_device(d_pix.data_ptr(), off, hs, ws, 0, effort, d_str.data_ptr(), cap)
+        assert rc == 0 and int(so[-1]) > 0
+        st, rc = codec.decode_device(d_str.data_ptr(), so, d_dec.data_ptr(), off, pix_cap=np.full(n, h * w, np.uint64))
+        assert rc == 0 and torch.equal(d_dec, d_pix)
+
+
+def test_legacy_decompress_on_an_exact_size_guarded_buffer(api, kodak):
+    """NBLICdecompress / QNBLICdecompress get no stream length (NBLIC.h:72, QNBLIC.h:14).  Without the side-channel
+    hint the wrappers may not read past the caller's mapping: the stream ends exactly at an inaccessible page."""
+    import ctypes as C
+    import mmap
+    lib = api.load_library()
+    libc = C.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    img = kodak["05"][:120, :200].copy()
+    page = mmap.PAGESIZE
+    for data, kind in ((api.legacy.nblic_compress(img, 0, 1)[0], "n"), (api.legacy.qnblic_compress(img), "q")):
+        size = (len(data) + page - 1) // page * page
+        m = mmap.mmap(-1, size + page)
+        base = C.addressof(C.c_char.from_buffer(m))
+        start = size - len(data)  # stream ends exactly where the protected page begins
+        if kind == "q" and (start & 1):
+            start -= 1  # QNBLIC words are 2-byte aligned; one spare byte then
+        m[start:start + len(data)] = data
+        assert libc.mprotect(base + size, page, 0) == 0  # PROT_NONE
+        out = np.zeros(img.size, np.uint8)
+        hh, ww, nn, ee = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        lib.nblic_b200_hint_input_len(0)
+        if kind == "n":
+            rc = lib.NBLICdecompress(0, C.cast(base + start, C.POINTER(C.c_uint8)), out.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                     C.byref(hh), C.byref(ww), C.byref(nn), C.byref(ee))
+        else:
+            rc = lib.QNBLICdecompress(C.cast(base + start, C.POINTER(C.c_uint16)), out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(hh), C.byref(ww))
+        assert rc == 0 and (hh.value, ww.value) == img.shape and np.array_equal(out.reshape(img.shape), img), kind
+        libc.mprotect(base + size, page, 3)
+        del base
+        m.close()
+
+
+def test_named_configs_2_and_3_synthetic(api, manifest):
+    """BASELINE.json configs[2] (synthetic 4096x4096 -n0 -e3) and the synthetic half of configs[3] (2048x2048 -n2 -e2):
+    stream bytes and hashes equal the unmodified reference's (tests/golden/manifest.json), the
+    reconstruction hash matches, and decoding returns the source / the reconstruction.  Every image is one serial
+    coder stream, so both run at the same time on two contexts (two host threads)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def run(h, w, near, effort):
+        c = api.Codec(0)
+        try:
+            img = gen(h, w, 0)
+            ent = manifest["synthetic"][f"{h}x{w}_s0"]["streams"][f"e{effort}n{near}"]
+            streams, recs, status = c.encode_batch([img], near, effort, want_recon=near > 0)
+            assert status == [api.OK]
+            assert (len(streams[0]), sha(streams[0])) == (ent["bytes"], ent["sha256"]), (h, w, near, effort)
+            if near:
+                assert sha(recs[0].tobytes()) == ent["recon_sha256"]
+                assert int(np.abs(recs[0].astype(int) - img.astype(int)).max()) <= near
+            d = c.decode_batch(streams)[0]
+            assert d is not None and (d[1], d[2]) == (near, effort)
+            assert np.array_equal(d[0], recs[0] if near else img)
+            return len(streams[0])
+        finally:
+            c.close()
+
+    with ThreadPoolExecutor(2) as pool:
+        big = os.environ.get("NBLIC_SKIP_4096") is None  # development runs may skip the ten-minute half; the default runs both
+        a = pool.submit(run, 4096, 4096, 0, 3) if big else None
+        b = pool.submit(run, 2048, 2048, 2, 2)
+        assert b.result() == 707198  # SURVEY.md 8(d) config 4
+        assert not big or a.result() == 7260363  # SURVEY.md 8(d) config 3

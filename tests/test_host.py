@@ -56,6 +56,49 @@ def test_peek_and_bound(lib):
     assert api.stream_bound(512, 768) >= 2 * 512 * 768
 
 
+def test_legacy_decode_never_reads_past_the_callers_mapping(tmp_path):
+    """The reference decode ABI carries no stream length (NBLIC.h:72); the drop-in wrappers bound their read by the
+    readable extent of p_buf.  readable_prefix() is exercised on a buffer that ends at an inaccessible page."""
+    import subprocess
+    src = tmp_path / "probe.c"
+    src.write_text(r"""
+#define _GNU_SOURCE
+#include <sys/mman.h>
+#include "%s"
+/* the batch ABI is not linked into this probe */
+nblic_b200_ctx *nblic_b200_create(int d) { (void)d; return 0; }
+const char *nblic_b200_last_error(const nblic_b200_ctx *c) { (void)c; return ""; }
+size_t nblic_b200_stream_bound(int h, int w) { return 2 * (size_t)h * w + 8192; }
+int nblic_b200_peek(const uint8_t *s, size_t n, int *h, int *w, int *a, int *e) { (void)s; (void)n; (void)h; (void)w; (void)a; (void)e; return -1; }
+int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *i, const int *h, const int *w, int a, int e, uint8_t *const *o,
+                            const size_t *oc, size_t *ol, uint8_t *const *r, int *s) { (void)c; (void)n; (void)i; (void)h; (void)w; (void)a; (void)e; (void)o; (void)oc; (void)ol; (void)r; (void)s; return -1; }
+int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *st, const size_t *sl, uint8_t *const *im, const size_t *ic, int *h,
+                            int *w, int *a, int *e, int *s) { (void)c; (void)n; (void)st; (void)sl; (void)im; (void)ic; (void)h; (void)w; (void)a; (void)e; (void)s; return -1; }
+int main(void) {
+    const size_t page = 4096, pages = 40;
+    uint8_t *m = mmap(0, (pages + 1) * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    size_t got = 0, k;
+    uint8_t *copy;
+    if (m == MAP_FAILED) return 2;
+    for (k = 0; k < pages * page; k++) m[k] = (uint8_t)(k * 7 + 3);
+    if (mprotect(m + pages * page, page, PROT_NONE)) return 3;
+    copy = readable_prefix(m + 100, 10 * pages * page, &got);          /* asks for far more than is readable */
+    if (!copy || got != pages * page - 100 || memcmp(copy, m + 100, got)) return 4;
+    free(copy);
+    copy = readable_prefix(m + 5, 70000, &got);                          /* fully readable request */
+    if (!copy || got != 70000 || memcmp(copy, m + 5, got)) return 5;
+    free(copy);
+    copy = readable_prefix(m + pages * page, 64, &got);                  /* nothing readable */
+    if (!copy || got != 0) return 6;
+    free(copy);
+    return 0;
+}
+""" % os.path.join(ROOT, "nblic_image_compression_b200", "csrc", "nblic_dropin.c"))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-O1", "-std=gnu99", "-Wall", "-o", str(exe), str(src), "-lpthread"], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
 def test_no_gpu_means_failure_not_fallback(lib):
     import torch
     if torch.cuda.is_available():

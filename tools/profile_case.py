@@ -11,8 +11,7 @@ reps = int(sys.argv[7]) if len(sys.argv) > 7 else 1
 codec = api.Codec(0, mapping)
 npx = h * w
 d_pix = torch.empty(n * npx, dtype=torch.uint8, device="cuda:0")
-for i in range(n):
-    codec.synth_device(d_pix.data_ptr() + i * npx, h, w, i)
+codec.synth_device_batch(d_pix.data_ptr(), n, h, w, 0)
 cap = n * api.stream_bound(h, w)
 d_str = torch.empty(cap, dtype=torch.uint8, device="cuda:0")
 d_dec = torch.empty(n * npx, dtype=torch.uint8, device="cuda:0")
