@@ -244,17 +244,17 @@ __global__ void __launch_bounds__(1024) scan_lengths_kernel(const Task *tasks, i
     if (threadIdx.x == 0) offsets[n] = carry;
 }
 
-/* Pack the streams: CTA (chunk, image) copies up to `chunk` bytes of image's stream.  The head comes
- * from the start of the slot, the tail from its end. */
+/* Pack the streams: CTA (image, piece) copies up to `chunk` bytes of image's stream.  The head comes
+ * from the start of the slot, the tail from its end.  The image index rides gridDim.x (no 65535 limit). */
 __global__ void __launch_bounds__(256) gather_streams_kernel(const Task *tasks, const unsigned long long *offsets, uint8_t *out,
                                                              unsigned long long out_cap, u32 chunk, int *overflow) {
-    const Task &t = tasks[blockIdx.y];
+    const Task &t = tasks[blockIdx.x];
     const u32 total = t.head_len + t.tail_len;
-    const u32 begin = blockIdx.x * chunk;
+    const u32 begin = blockIdx.y * chunk;
     if (begin >= total) return;
     const u32 end = min(total, begin + chunk);
-    const unsigned long long dst0 = offsets[blockIdx.y];
-    if (dst0 + total > out_cap) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(overflow, 1); return; }
+    const unsigned long long dst0 = offsets[blockIdx.x];
+    if (dst0 + total > out_cap) { if (threadIdx.x == 0 && blockIdx.y == 0) atomicExch(overflow, 1); return; }
     const uint8_t *tail = t.slot + (t.slot_cap & ~1u) - t.tail_len;
     for (u32 k = begin + threadIdx.x; k < end; k += blockDim.x)
         out[dst0 + k] = k < t.head_len ? t.slot[k] : tail[k - t.head_len];
