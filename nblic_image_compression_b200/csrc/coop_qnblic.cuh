@@ -78,6 +78,8 @@ NB_DEV u32 q_finish_histograms(u32 *tab, uint16_t *out, u32 o, u32 cap, int lane
     return o + total;
 }
 
+__device__ bool coop_q_finish(const uint16_t *sym, int h, int w, uint16_t *out, u32 cap, u32 *tab, int lane, u32 &head_words, u32 &tail_words);
+
 __device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u32 cap, uint8_t *sym8, QCoopSmem &sm, u32 *tab, int lane,
                               u32 &head_words, u32 &tail_words) {
     uint16_t *sym = reinterpret_cast<uint16_t *>(sym8); /* cls | y << 8 per pixel, raster order */
@@ -134,7 +136,13 @@ __device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u
         }
     }
     __syncwarp();
+    return coop_q_finish(sym, h, w, out, cap, tab, lane, head_words, tail_words);
+}
 
+/* Second half of the encoder: header, the 12 histogram descriptions, and pass 2 (the reverse rANS sweep) over the
+ * (class | y << 8) symbols of pass 1 and their counts in `tab`.  One warp; also the final stage of the
+ * whole-GPU single-image pipeline (pipe_qnblic.cuh). */
+__device__ bool coop_q_finish(const uint16_t *sym, int h, int w, uint16_t *out, u32 cap, u32 *tab, int lane, u32 &head_words, u32 &tail_words) {
     if (cap < 8) return false;
     if (lane == 0) { out[0] = 0x3051; out[1] = 0x322e; out[2] = (uint16_t)h; out[3] = (uint16_t)w; } /* R: QNBLIC.c:463-473 */
     const u32 o = q_finish_histograms(tab, out, 4, cap, lane);

@@ -38,6 +38,11 @@ struct Task {
     int h, w, near, k_step, effort;
 };
 
+} /* namespace */
+#include "subwarp_nblic.cuh" /* needs Task */
+#include "pipe_qnblic.cuh"
+namespace {
+
 constexpr int kChunkImagesPerSm = 192; /* host-buffer API: images per pipeline chunk and SM (multiple of 8, 16 and 24) */
 constexpr int N_STATE_BYTES = N_CTX_ENTRIES * 2 + N_FOREST_ENTRIES * 4 + N_RANK_ENTRIES * 2 + N_RANK_ENTRIES * 4; /* 81920 */
 constexpr int N_SMEM_BYTES = N_CTX_ENTRIES * 2 + N_FOREST_ENTRIES * 4 + N_RANK_ENTRIES * 2;                       /* 40960 */
@@ -182,6 +187,22 @@ __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *
     }
 }
 
+/* Effort-1 decoder with 32 / LPS streams per warp (subwarp_nblic.cuh).  `packs`: 32 / LPS task indices per entry
+ * (-1 = empty), all of one height x width; `scratch`: per CTA 32 / LPS x kSubScratchBytes. */
+template <int LPS, bool CTXG>
+__global__ void __launch_bounds__(32) subwarp_decode_kernel(Task *tasks, const int *packs, int n_packs, int *queue, uint8_t *scratch, int max_nodes) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x;
+    uint8_t *mine = scratch + (size_t)blockIdx.x * (32 / LPS) * kSubScratchBytes;
+    for (;;) {
+        int pos = lane == 0 ? atomicAdd(queue, 1) : 0;
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (pos >= n_packs) break;
+        subwarp_decode_pack<LPS, CTXG>(tasks, packs + (size_t)pos * (32 / LPS), smem, mine, max_nodes, lane);
+        __syncwarp();
+    }
+}
+
 /* Warp-cooperative QNBLIC kernel (coop_qnblic.cuh): one warp per CTA, bias table and the 12 histograms in
  * shared memory. */
 template <bool DEC>
@@ -204,6 +225,21 @@ __global__ void __launch_bounds__(32) coop_q_kernel(Task *tasks, const int *orde
             }
         }
         __syncwarp();
+    }
+}
+
+/* Last stage of the whole-GPU QNBLIC encode (pipe_qnblic.cuh): one warp per image finishes the stream from the
+ * symbols in t.sym and the counts in tabs[image]. */
+__global__ void __launch_bounds__(32) qpipe_finish_kernel(Task *tasks, const int *order, int n_order, u32 *tabs) {
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= n_order) return;
+    Task &t = tasks[order[blockIdx.x]];
+    u32 head = 0, tail = 0;
+    const bool ok = coop_q_finish(reinterpret_cast<const uint16_t *>(t.sym), t.h, t.w, reinterpret_cast<uint16_t *>(t.slot), t.slot_cap / 2,
+                                  tabs + (size_t)blockIdx.x * Q_TAB_ENTRIES, lane, head, tail);
+    if (lane == 0) {
+        if (ok) { t.head_len = head * 2; t.tail_len = tail * 2; }
+        else { t.status = NBLIC_B200_OVERFLOW; t.head_len = t.tail_len = 0; }
     }
 }
 

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/nblic_b200.h"
@@ -57,11 +58,15 @@ struct nblic_b200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy[2] = {nullptr, nullptr};
     std::string error;
     uint64_t launches = 0;
-    float coder_ms = 0.f;
+    float coder_ms = 0.f, coder_ms_total = 0.f; /* most recent batch call / accumulated by split_over_lanes */
     const char *last_map = "none";
     int last_slots = 0; /* resident streams the most recent cooperative launch could hold */
-    DevBuf tasks, order, queue, slots, sym, cold, coop_counts, avp, offsets, flags, pixels, streams, recon, peeks;
+    int sub_lps = getenv("NBLIC_B200_LPS") ? atoi(getenv("NBLIC_B200_LPS")) : 0; /* experiments: lanes per stream of the effort-1 decoder (32 = one stream per warp) */
+    bool sub_ctx_smem = getenv("NBLIC_B200_CTX_SMEM") != nullptr;
+    int qpipe = getenv("NBLIC_B200_QPIPE") ? atoi(getenv("NBLIC_B200_QPIPE")) : -1; /* experiments: force (1) / forbid (0) the whole-GPU QNBLIC encode */                   /* experiments: whole bias table in shared memory */
+    DevBuf tasks, order, queue, slots, sym, cold, coop_counts, sub_scratch, pipe_meta, pipe_sorted, pipe_counts, avp, offsets, flags, pixels, streams, recon, peeks;
     int occ_warp[2] = {0, 0};
+    nblic_b200_ctx *lane[2] = {nullptr, nullptr}; /* host-buffer calls on large batches: two sub-contexts coding alternate pieces (see split_over_lanes) */
 };
 
 namespace {
@@ -82,14 +87,10 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct LaunchPlan { int map; int grid; size_t cold_stride; size_t smem; };
 
-/* Persistent grid for n queued streams when `slots` can be resident: the number of waves is fixed by the residency,
- * but spreading the streams evenly over the waves (10 000 streams, 3 108 slots: 4 waves of 2 500 instead of 3 full
- * ones and a 22 % tail) leaves fewer streams competing for the issue slots of an SM in every wave. */
-int balanced_grid(int n, int slots) {
-    if (n <= slots) return std::max(n, 1);
-    const int waves = (n + slots - 1) / slots;
-    return (n + waves - 1) / waves;
-}
+/* Persistent grid for n queued streams when `slots` can be resident.  Measured (round 2): spreading 10 000 streams evenly
+ * over 4 waves of 2 500 instead of filling 3 108 slots made both effort-1 kernels 6 % SLOWER -- throughput grows with
+ * the resident warps (issue slots are only 62-66 % used), and the dynamic queue already packs the tail.  So: fill. */
+int balanced_grid(int n, int slots) { return std::max(1, std::min(n, slots)); }
 
 template <int KIND, bool DEC, int MAP>
 int launch_coder_t(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, const LaunchPlan &plan, size_t avp_stride) {
@@ -175,6 +176,88 @@ int launch_coop_t(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_que
     return 0;
 }
 
+/* QNBLIC encode of few (large) images: every image's front end, bias chains and symbol counts use the whole GPU, one
+ * launch sequence per image on the context's stream; a single launch then finishes all streams, one warp per image
+ * (pipe_qnblic.cuh).  `idx` are task indices in launch order, `d_order` the same list on the device. */
+int launch_qpipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, const std::vector<int> &idx, const int *d_order) {
+    const int n = (int)idx.size();
+    size_t max_px = 1, max_counts = 1;
+    auto chunking = [](size_t px, int &chunk_px, int &n_chunks) {
+        size_t cp = std::max<size_t>(4096, (px + 4095) / 4096);
+        cp = (cp + 31) / 32 * 32;
+        chunk_px = (int)cp;
+        n_chunks = (int)((px + cp - 1) / cp);
+    };
+    for (int i : idx) {
+        const size_t px = (size_t)tasks[(size_t)i].h * tasks[(size_t)i].w;
+        int chunk_px, n_chunks;
+        chunking(px, chunk_px, n_chunks);
+        max_px = std::max(max_px, px);
+        max_counts = std::max(max_counts, (size_t)kPipeKeys * n_chunks);
+    }
+    CK(c->pipe_meta.reserve(max_px * sizeof(u32)));
+    CK(c->pipe_sorted.reserve(max_px * sizeof(uint2)));
+    CK(c->pipe_counts.reserve((max_counts + kPipeKeys + 1) * sizeof(u32)));
+    CK(c->coop_counts.reserve((size_t)n * Q_TAB_ENTRIES * sizeof(u32)));
+    CK(cudaMemsetAsync(c->coop_counts.p, 0, (size_t)n * Q_TAB_ENTRIES * sizeof(u32), c->stream));
+    u32 *meta = (u32 *)c->pipe_meta.p, *counts = (u32 *)c->pipe_counts.p, *key_start = counts + max_counts;
+    uint2 *sorted = (uint2 *)c->pipe_sorted.p;
+    for (int k = 0; k < n; k++) {
+        const Task &t = tasks[(size_t)idx[(size_t)k]];
+        const long long px = (long long)t.h * t.w;
+        int chunk_px, n_chunks;
+        chunking((size_t)px, chunk_px, n_chunks);
+        const int front_blocks = 1 + (int)std::max<long long>(1, std::min<long long>((px + 255) / 256, (long long)c->sm_count * 8));
+        qpipe_front_kernel<<<front_blocks, 256, 0, c->stream>>>(t.src, t.h, t.w, meta);
+        qpipe_count_kernel<<<n_chunks, 256, 0, c->stream>>>(meta, px, chunk_px, n_chunks, counts);
+        qpipe_scan_kernel<<<1, 1024, 0, c->stream>>>(counts, n_chunks, key_start);
+        qpipe_scatter_kernel<<<n_chunks, 32, 0, c->stream>>>(meta, px, chunk_px, n_chunks, counts, sorted);
+        qpipe_chain_kernel<<<(kPipeKeys + 127) / 128, 128, 0, c->stream>>>(sorted, key_start, reinterpret_cast<uint16_t *>(t.sym),
+                                                                         (u32 *)c->coop_counts.p + (size_t)k * Q_TAB_ENTRIES);
+        c->launches += 5;
+    }
+    qpipe_finish_kernel<<<n, 32, 0, c->stream>>>((Task *)c->tasks.p, d_order, n, (u32 *)c->coop_counts.p);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+/* Effort-1 decode with 32 / LPS streams per warp.  probe_only: just report the resident streams. */
+template <int LPS, bool CTXG>
+int launch_subwarp_t(nblic_b200_ctx *c, int n_packs, const int *d_packs, int *d_queue, int max_nodes, bool probe_only, int *slots_out) {
+    const size_t smem = SubLayout<LPS, CTXG>::bytes(max_nodes);
+    auto kern = subwarp_decode_kernel<LPS, CTXG>;
+    int per_sm = 0;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    const int warps = c->sm_count * std::max(per_sm, 1);
+    if (slots_out) *slots_out = warps * (32 / LPS);
+    if (probe_only) return 0;
+    const int grid = balanced_grid(n_packs, warps);
+    CK(c->sub_scratch.reserve((size_t)grid * (32 / LPS) * kSubScratchBytes));
+    kern<<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_packs, n_packs, d_queue, (uint8_t *)c->sub_scratch.p, max_nodes);
+    c->launches++;
+    c->last_slots = warps * (32 / LPS);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int launch_subwarp(nblic_b200_ctx *c, int lps, int n_packs, const int *d_packs, int *d_queue, int max_nodes) {
+    if (c->sub_ctx_smem) {
+        if (lps == 8) return launch_subwarp_t<8, false>(c, n_packs, d_packs, d_queue, max_nodes, false, nullptr);
+        return launch_subwarp_t<16, false>(c, n_packs, d_packs, d_queue, max_nodes, false, nullptr);
+    }
+    if (lps == 8) return launch_subwarp_t<8, true>(c, n_packs, d_packs, d_queue, max_nodes, false, nullptr);
+    return launch_subwarp_t<16, true>(c, n_packs, d_packs, d_queue, max_nodes, false, nullptr);
+}
+
+/* Lanes per stream for an effort-1 decode of n streams: several streams per warp pay when the streams outnumber what
+ * the one-stream-per-warp kernel keeps resident (issue-bound regime); below that, a stream alone in its warp is faster. */
+int choose_sub_lps(nblic_b200_ctx *c, int n_streams) {
+    if (c->sub_lps == 8 || c->sub_lps == 16 || c->sub_lps == 32) return c->sub_lps;
+    return n_streams >= c->sm_count * 16 ? 8 : 32;
+}
+
 /* Efforts 2/3 always keep the rank tables in L2.  Effort 1 keeps them in shared memory (lowest latency per
  * pixel) unless the batch has more images than that layout can hold resident; then the L2 layout more than
  * doubles the resident streams. */
@@ -221,14 +304,35 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
         start[g] = order.size();
         order.insert(order.end(), group[g].begin(), group[g].end());
     }
+    /* effort-1 decode with several streams per warp: packs of equal-size streams (the list is sorted by size) */
+    const int sub_lps = DEC && !group[G_FB1].empty() ? choose_sub_lps(c, (int)group[G_FB1].size()) : 32;
+    const size_t packs_at = order.size();
+    int n_packs = 0;
+    if (sub_lps < 32) {
+        const int spw = 32 / sub_lps;
+        const std::vector<int> &g = group[G_FB1];
+        for (size_t at = 0; at < g.size();) {
+            const Task &first = tasks[(size_t)g[at]];
+            int k = 0;
+            for (; k < spw && at + k < g.size(); k++) {
+                const Task &t = tasks[(size_t)g[at + k]];
+                if (t.h != first.h || t.w != first.w) break;
+                order.push_back(g[at + k]);
+            }
+            for (int pad = k; pad < spw; pad++) order.push_back(-1);
+            at += (size_t)k;
+            n_packs++;
+        }
+    }
     CK(c->tasks.reserve(sizeof(Task) * (size_t)std::max(n, 1)));
-    CK(c->order.reserve(sizeof(int) * (size_t)std::max(n, 1)));
+    CK(c->order.reserve(sizeof(int) * std::max<size_t>(order.size(), 1)));
     CK(c->queue.reserve(N_GROUPS * sizeof(int)));
     CK(cudaMemcpyAsync(c->tasks.p, tasks.data(), sizeof(Task) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     if (!order.empty()) CK(cudaMemcpyAsync(c->order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->queue.p, 0, N_GROUPS * sizeof(int), c->stream));
 
     CK(cudaEventRecord(c->ev0, c->stream));
+    bool pipelined = false;
     for (int g = 0; g < N_GROUPS; g++) {
         if (group[g].empty()) continue;
         const int cnt = (int)group[g].size();
@@ -236,15 +340,24 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
         int *d_q = (int *)c->queue.p + g;
         int rc = 0;
         switch (g) {
-            case G_Q: rc = coop_ok ? launch_coop_q<DEC>(c, cnt, d_ord, d_q) : launch_coder<KIND_Q, DEC>(c, cnt, d_ord, d_q, 1, 0); break;
+            case G_Q:
+                /* few images: one warp per image would leave the GPU empty and the front end on the critical path */
+                if (!DEC && coop_ok && (c->qpipe == 1 || (c->qpipe != 0 && cnt <= 64))) { rc = launch_qpipe_encode(c, tasks, group[g], d_ord); pipelined = true; }
+                else rc = coop_ok ? launch_coop_q<DEC>(c, cnt, d_ord, d_q) : launch_coder<KIND_Q, DEC>(c, cnt, d_ord, d_q, 1, 0);
+                break;
             case G_SEQ: rc = launch_coder<KIND_N, DEC>(c, cnt, d_ord, d_q, max_w[g], seq_effort); break;
             case G_E1_LOSSLESS: rc = launch_coop<0, 0>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
-            case G_FB1: rc = launch_coop<0, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
+            case G_FB1:
+                if (sub_lps < 32) rc = launch_subwarp(c, sub_lps, n_packs, (const int *)c->order.p + packs_at, d_q, max_nodes[g]);
+                else rc = launch_coop<0, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]);
+                break;
             case G_FB2: rc = launch_coop<6, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
             case G_FB3: rc = launch_coop<10, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
         }
         if (rc) return -1;
         if (g >= G_E1_LOSSLESS || (g == G_Q && coop_ok)) c->last_map = "warp-coop";
+        if (g == G_Q && pipelined) c->last_map = "gpu-pipeline";
+        if (g == G_FB1 && sub_lps < 32) c->last_map = sub_lps == 8 ? "4-streams-per-warp" : "2-streams-per-warp";
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     return 0;
@@ -303,10 +416,11 @@ nblic_b200_ctx *nblic_b200_create(int device) {
 
 void nblic_b200_destroy(nblic_b200_ctx *c) {
     if (!c) return;
+    for (nblic_b200_ctx *&l : c->lane) { nblic_b200_destroy(l); l = nullptr; }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy) cudaStreamSynchronize(c->copy);
-    DevBuf *bufs[] = {&c->tasks, &c->order, &c->queue, &c->slots, &c->sym, &c->cold, &c->coop_counts, &c->avp, &c->offsets, &c->flags, &c->pixels, &c->streams, &c->recon, &c->peeks};
+    DevBuf *bufs[] = {&c->tasks, &c->order, &c->queue, &c->slots, &c->sym, &c->cold, &c->coop_counts, &c->sub_scratch, &c->pipe_meta, &c->pipe_sorted, &c->pipe_counts, &c->avp, &c->offsets, &c->flags, &c->pixels, &c->streams, &c->recon, &c->peeks};
     for (DevBuf *b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -321,10 +435,16 @@ const char *nblic_b200_last_error(const nblic_b200_ctx *c) { return c ? c->error
 int nblic_b200_set_mapping(nblic_b200_ctx *c, int mapping) {
     if (!c || mapping < NBLIC_B200_MAP_AUTO || mapping > NBLIC_B200_MAP_LANE) return -1;
     c->mapping = mapping;
+    for (nblic_b200_ctx *l : c->lane) if (l) l->mapping = mapping;
     return 0;
 }
 
-uint64_t nblic_b200_launch_count(const nblic_b200_ctx *c) { return c ? c->launches : 0; }
+uint64_t nblic_b200_launch_count(const nblic_b200_ctx *c) {
+    if (!c) return 0;
+    uint64_t total = c->launches;
+    for (const nblic_b200_ctx *l : c->lane) if (l) total += l->launches;
+    return total;
+}
 float nblic_b200_last_coder_ms(const nblic_b200_ctx *c) { return c ? c->coder_ms : 0.f; }
 const char *nblic_b200_last_mapping(const nblic_b200_ctx *c) { return c ? c->last_map : "none"; }
 int nblic_b200_last_slots(const nblic_b200_ctx *c) { return c ? c->last_slots : 0; }
@@ -459,8 +579,8 @@ int nblic_b200_decode_batch_device(nblic_b200_ctx *c, int n, const uint8_t *d_st
     return decode_device_impl(c, n, d_streams, stream_off, lens.data(), d_pixels, pix_off, pix_cap, status);
 }
 
-int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *images, const int *heights, const int *widths, int near,
-                            int effort, uint8_t *const *outs, const size_t *out_caps, size_t *out_lens, uint8_t *const *recon, int *status) {
+static int encode_batch_one_lane(nblic_b200_ctx *c, int n, const uint8_t *const *images, const int *heights, const int *widths, int near,
+                                 int effort, uint8_t *const *outs, const size_t *out_caps, size_t *out_lens, uint8_t *const *recon, int *status) {
     if (!c) return -1;
     if (n < 0 || (n > 0 && (!images || !heights || !widths || !outs || !out_caps || !out_lens))) { fail(c, "bad arguments"); return -1; }
     CK(cudaSetDevice(c->device));
@@ -544,8 +664,8 @@ int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *imag
     return failed;
 }
 
-int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *streams, const size_t *stream_lens, uint8_t *const *images,
-                            const size_t *img_caps, int *heights, int *widths, int *nears, int *efforts, int *status) {
+static int decode_batch_one_lane(nblic_b200_ctx *c, int n, const uint8_t *const *streams, const size_t *stream_lens, uint8_t *const *images,
+                                 const size_t *img_caps, int *heights, int *widths, int *nears, int *efforts, int *status) {
     if (!c) return -1;
     if (n < 0 || (n > 0 && (!streams || !stream_lens || !images || !img_caps))) { fail(c, "bad arguments"); return -1; }
     CK(cudaSetDevice(c->device));
@@ -619,6 +739,75 @@ int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *stre
     c->coder_ms = coder_ms;
     CK(cudaStreamSynchronize(c->copy));
     return failed;
+}
+
+/*
+ * Host-buffer calls on large batches.  One lane = upload a piece, code it, download it, all on its own streams and
+ * scratch.  Two lanes (two sub-contexts, one host thread each) take alternate pieces of the batch, so the PCIe traffic
+ * of one piece rides under the kernels of the other, and the persistent grid of the next piece fills the SMs as the
+ * previous one drains -- no kernel ever waits for another.  A piece is 24 images per SM: at least one full wave of every
+ * coder kernel, small enough that the first upload and the last download (the only exposed copies) stay short.
+ */
+constexpr int kLaneImagesPerSm = 24;
+
+} /* extern "C" */
+
+template <class Piece>
+static int split_over_lanes(nblic_b200_ctx *c, int n, Piece piece) {
+    const int piece_n = c->sm_count * kLaneImagesPerSm;
+    for (nblic_b200_ctx *&l : c->lane) {
+        if (!l) l = nblic_b200_create(c->device);
+        if (!l) { fail(c, "lane context: %s", g_create_error.c_str()); return -1; }
+        l->mapping = c->mapping;
+        l->coder_ms_total = 0.f;
+    }
+    const int n_pieces = (n + piece_n - 1) / piece_n;
+    int result[2] = {0, 0};
+    auto work = [&](int who) {
+        for (int k = who; k < n_pieces; k += 2) {
+            const int lo = k * piece_n, cnt = std::min(n - lo, piece_n);
+            const int rc = piece(c->lane[who], lo, cnt);
+            if (rc < 0) { result[who] = -1; return; }
+            result[who] += rc;
+        }
+    };
+    std::thread other(work, 1);
+    work(0);
+    other.join();
+    c->coder_ms = 0.f;
+    for (nblic_b200_ctx *l : c->lane) { c->coder_ms += l->coder_ms_total; c->last_map = l->last_map; c->last_slots = l->last_slots; }
+    CK(cudaSetDevice(c->device));
+    if (result[0] < 0 || result[1] < 0) { fail(c, "%s", (result[0] < 0 ? c->lane[0] : c->lane[1])->error.c_str()); return -1; }
+    return result[0] + result[1];
+}
+
+extern "C" {
+
+int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *images, const int *heights, const int *widths, int near,
+                            int effort, uint8_t *const *outs, const size_t *out_caps, size_t *out_lens, uint8_t *const *recon, int *status) {
+    if (!c) return -1;
+    if (n <= c->sm_count * kLaneImagesPerSm) return encode_batch_one_lane(c, n, images, heights, widths, near, effort, outs, out_caps, out_lens, recon, status);
+    if (!images || !heights || !widths || !outs || !out_caps || !out_lens) { fail(c, "bad arguments"); return -1; }
+    return split_over_lanes(c, n, [&](nblic_b200_ctx *l, int lo, int cnt) {
+        const int rc = encode_batch_one_lane(l, cnt, images + lo, heights + lo, widths + lo, near, effort, outs + lo, out_caps + lo, out_lens + lo,
+                                             recon ? recon + lo : nullptr, status ? status + lo : nullptr);
+        l->coder_ms_total += l->coder_ms;
+        return rc;
+    });
+}
+
+int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *streams, const size_t *stream_lens, uint8_t *const *images,
+                            const size_t *img_caps, int *heights, int *widths, int *nears, int *efforts, int *status) {
+    if (!c) return -1;
+    if (n <= c->sm_count * kLaneImagesPerSm) return decode_batch_one_lane(c, n, streams, stream_lens, images, img_caps, heights, widths, nears, efforts, status);
+    if (!streams || !stream_lens || !images || !img_caps) { fail(c, "bad arguments"); return -1; }
+    return split_over_lanes(c, n, [&](nblic_b200_ctx *l, int lo, int cnt) {
+        const int rc = decode_batch_one_lane(l, cnt, streams + lo, stream_lens + lo, images + lo, img_caps + lo, heights ? heights + lo : nullptr,
+                                             widths ? widths + lo : nullptr, nears ? nears + lo : nullptr, efforts ? efforts + lo : nullptr,
+                                             status ? status + lo : nullptr);
+        l->coder_ms_total += l->coder_ms;
+        return rc;
+    });
 }
 
 int nblic_b200_debug_divcheck(nblic_b200_ctx *c, const int64_t *num, const int64_t *den, int n, int64_t *out) {
