@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libnblic_b200.so")
 CLI = os.path.join(HERE, "nblic_batch")  # batch command-line front end (csrc/nblic_batch_cli.c)
 SOURCES_CU = ["stream_kernels.cu"]
 SOURCES_C = ["nblic_dropin.c"]
-HEADERS = [os.path.join(CSRC, h) for h in ("codec_core.cuh", "coop_nblic.cuh", "coop_avp.cuh", "coop_qnblic.cuh", "kernels.cuh", "nblic_batch_cli.c")] + \
+HEADERS = [os.path.join(CSRC, h) for h in sorted(os.listdir(CSRC)) if h.endswith((".cuh", ".h", ".c"))] + \
           [os.path.join(HERE, "..", "include", "nblic_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=false"]

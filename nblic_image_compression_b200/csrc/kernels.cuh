@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *
 
 /* Effort-1 decoder with 32 / LPS streams per warp (subwarp_nblic.cuh).  `packs`: 32 / LPS task indices per entry
  * (-1 = empty), all of one height x width; `scratch`: per CTA 32 / LPS x kSubScratchBytes. */
-template <int LPS, bool CTXG>
+template <int LPS, bool FORESTG>
 __global__ void __launch_bounds__(32) subwarp_decode_kernel(Task *tasks, const int *packs, int n_packs, int *queue, uint8_t *scratch, int max_nodes) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(32) subwarp_decode_kernel(Task *tasks, const i
         int pos = lane == 0 ? atomicAdd(queue, 1) : 0;
         pos = __shfl_sync(0xffffffffu, pos, 0);
         if (pos >= n_packs) break;
-        subwarp_decode_pack<LPS, CTXG>(tasks, packs + (size_t)pos * (32 / LPS), smem, mine, max_nodes, lane);
+        subwarp_decode_pack<LPS, FORESTG>(tasks, packs + (size_t)pos * (32 / LPS), smem, mine, max_nodes, lane);
         __syncwarp();
     }
 }

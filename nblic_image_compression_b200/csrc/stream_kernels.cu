@@ -62,7 +62,7 @@ struct nblic_b200_ctx {
     const char *last_map = "none";
     int last_slots = 0; /* resident streams the most recent cooperative launch could hold */
     int sub_lps = getenv("NBLIC_B200_LPS") ? atoi(getenv("NBLIC_B200_LPS")) : 0; /* experiments: lanes per stream of the effort-1 decoder (32 = one stream per warp) */
-    bool sub_ctx_smem = getenv("NBLIC_B200_CTX_SMEM") != nullptr;
+    bool sub_forest_smem = getenv("NBLIC_B200_FOREST_SMEM") != nullptr;            /* experiments: counter forest in shared memory instead of L2 */
     int qpipe = getenv("NBLIC_B200_QPIPE") ? atoi(getenv("NBLIC_B200_QPIPE")) : -1; /* experiments: force (1) / forbid (0) the whole-GPU QNBLIC encode */                   /* experiments: whole bias table in shared memory */
     DevBuf tasks, order, queue, slots, sym, cold, coop_counts, sub_scratch, pipe_meta, pipe_sorted, pipe_counts, avp, offsets, flags, pixels, streams, recon, peeks;
     int occ_warp[2] = {0, 0};
@@ -222,17 +222,15 @@ int launch_qpipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, const
     return 0;
 }
 
-/* Effort-1 decode with 32 / LPS streams per warp.  probe_only: just report the resident streams. */
-template <int LPS, bool CTXG>
-int launch_subwarp_t(nblic_b200_ctx *c, int n_packs, const int *d_packs, int *d_queue, int max_nodes, bool probe_only, int *slots_out) {
-    const size_t smem = SubLayout<LPS, CTXG>::bytes(max_nodes);
-    auto kern = subwarp_decode_kernel<LPS, CTXG>;
+/* Effort-1 decode with 32 / LPS streams per warp; FORESTG: counter forest in L2 instead of shared memory. */
+template <int LPS, bool FORESTG>
+int launch_subwarp_t(nblic_b200_ctx *c, int n_packs, const int *d_packs, int *d_queue, int max_nodes) {
+    const size_t smem = SubLayout<LPS, FORESTG>::bytes(max_nodes);
+    auto kern = subwarp_decode_kernel<LPS, FORESTG>;
     int per_sm = 0;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
     const int warps = c->sm_count * std::max(per_sm, 1);
-    if (slots_out) *slots_out = warps * (32 / LPS);
-    if (probe_only) return 0;
     const int grid = balanced_grid(n_packs, warps);
     CK(c->sub_scratch.reserve((size_t)grid * (32 / LPS) * kSubScratchBytes));
     kern<<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_packs, n_packs, d_queue, (uint8_t *)c->sub_scratch.p, max_nodes);
@@ -243,18 +241,15 @@ int launch_subwarp_t(nblic_b200_ctx *c, int n_packs, const int *d_packs, int *d_
 }
 
 int launch_subwarp(nblic_b200_ctx *c, int lps, int n_packs, const int *d_packs, int *d_queue, int max_nodes) {
-    if (c->sub_ctx_smem) {
-        if (lps == 8) return launch_subwarp_t<8, false>(c, n_packs, d_packs, d_queue, max_nodes, false, nullptr);
-        return launch_subwarp_t<16, false>(c, n_packs, d_packs, d_queue, max_nodes, false, nullptr);
-    }
-    if (lps == 8) return launch_subwarp_t<8, true>(c, n_packs, d_packs, d_queue, max_nodes, false, nullptr);
-    return launch_subwarp_t<16, true>(c, n_packs, d_packs, d_queue, max_nodes, false, nullptr);
+    (void)lps;
+    if (c->sub_forest_smem) return launch_subwarp_t<8, false>(c, n_packs, d_packs, d_queue, max_nodes);
+    return launch_subwarp_t<8, true>(c, n_packs, d_packs, d_queue, max_nodes);
 }
 
 /* Lanes per stream for an effort-1 decode of n streams: several streams per warp pay when the streams outnumber what
  * the one-stream-per-warp kernel keeps resident (issue-bound regime); below that, a stream alone in its warp is faster. */
 int choose_sub_lps(nblic_b200_ctx *c, int n_streams) {
-    if (c->sub_lps == 8 || c->sub_lps == 16 || c->sub_lps == 32) return c->sub_lps;
+    if (c->sub_lps == 8 || c->sub_lps == 32) return c->sub_lps;
     return n_streams >= c->sm_count * 16 ? 8 : 32;
 }
 
@@ -357,7 +352,7 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
         if (rc) return -1;
         if (g >= G_E1_LOSSLESS || (g == G_Q && coop_ok)) c->last_map = "warp-coop";
         if (g == G_Q && pipelined) c->last_map = "gpu-pipeline";
-        if (g == G_FB1 && sub_lps < 32) c->last_map = sub_lps == 8 ? "4-streams-per-warp" : "2-streams-per-warp";
+        if (g == G_FB1 && sub_lps < 32) c->last_map = "4-streams-per-warp";
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     return 0;

@@ -15,9 +15,11 @@
  * Shared memory per stream is what bounds the resident streams, so the bias table (R: NBLIC.c:60-64, 4 KB) moves to
  * global memory / L2 and only the 256-entry row of the current activity class pair sits in shared memory: the row is
  * known before the predictor runs, is fetched with cp.async (16-byte LDGSTS) behind it, and entries are written
- * through.  The rank tables and their frequencies already live in L2 (coop_nblic.cuh, RG).  What stays in shared
- * memory: the compacted counter forest (4 KB lossless), the row cache (512 B), the phase-P records (32 B x LPS).
- *
+ * through.  The rank tables and their frequencies already live in L2 (coop_nblic.cuh, RG).  With FORESTG the compacted
+ * counter forest (4 KB lossless) goes to L2 as well: the first round's candidates are requested before the predictor
+ * runs, so only the suffix round pays an L2 round trip (~250 cycles of a ~4000-cycle pixel) -- and a warp then needs
+ * 3 KB of shared memory instead of 20 KB, so every stream of a 10 000-image batch is resident at once (17 warps per SM
+ * instead of 11, no second wave).
  * Every arithmetic step is the one coop_feedback<0, true, RG> performs (same helpers); the streams produced by the
  * encoders decode to the same pixels.  R: NBLIC.c:749-908 (decode branch), :640-679 (Zcodec), :527-586 (coder).
  */
@@ -26,19 +28,22 @@
 
 namespace nblic {
 
-/* global scratch of one stream: rank-mapper frequencies [512][20] int, rank tables [512][20] bytes, bias table [2048] int16 */
-constexpr size_t kSubCountOff = 0, kSubRankOff = (size_t)N_RANK_ENTRIES * 4, kSubCtxOff = kSubRankOff + N_RANK_ENTRIES;
-constexpr size_t kSubScratchBytes = kSubCtxOff + (size_t)N_CTX_ENTRIES * 2; /* 55 296 */
+/* global scratch of one stream: rank-mapper frequencies [512][20] int, rank -> symbol tables [512][32] bytes (20 used: rows are
+ * 16-byte aligned for cp.async), bias table [2048] int16, counter forest [16 * 256] u32 (used when FORESTG) */
+constexpr int kSubRankStride = 32;
+constexpr size_t kSubCountOff = 0, kSubRankOff = (size_t)N_RANK_ENTRIES * 4, kSubCtxOff = kSubRankOff + 512 * kSubRankStride;
+constexpr size_t kSubForestOff = kSubCtxOff + (size_t)N_CTX_ENTRIES * 2;
+constexpr size_t kSubScratchBytes = kSubForestOff + (size_t)N_FOREST_ENTRIES * 4; /* 77 824 */
 
-template <int LPS, bool CTXG> struct SubLayout {
+template <int LPS, bool FORESTG> struct SubLayout {
     static constexpr int SPW = 32 / LPS;
-    static constexpr int kCtxEntries = CTXG ? 256 : N_CTX_ENTRIES; /* per stream, int16 */
-    static constexpr size_t kSoftOff = 0;                                          /* uint16 soft[208], shared by the streams */
+    static constexpr size_t kSoftOff = 0;                                          /* uint16 soft[208], shared by the streams  */
     static constexpr size_t kFbaseOff = 416;                                       /* uint16 fbase[SPW][16]                    */
-    static constexpr size_t kRecOff = (kFbaseOff + SPW * 32 + 15) & ~(size_t)15;   /* PixRec recs[LPS][SPW]                    */
-    static constexpr size_t kCtxOff = kRecOff + sizeof(PixRec) * 32;               /* int16 ctx[SPW][kCtxEntries]              */
-    static constexpr size_t kForestOff = kCtxOff + (size_t)SPW * kCtxEntries * 2;  /* u32 forest[SPW][max_nodes]               */
-    static size_t bytes(int max_nodes) { return kForestOff + (size_t)SPW * max_nodes * 4; }
+    static constexpr size_t kRankOff = (kFbaseOff + SPW * 32 + 15) & ~(size_t)15;  /* per stream: int count[20], u8 sym[32] = 112 B */
+    static constexpr size_t kRecOff = kRankOff + SPW * 112;                        /* PixRec recs[LPS][SPW]                    */
+    static constexpr size_t kCtxOff = kRecOff + sizeof(PixRec) * 32;               /* int16 ctx[SPW][256]: row cache           */
+    static constexpr size_t kForestOff = kCtxOff + (size_t)SPW * 256 * 2;          /* u32 forest[SPW][max_nodes] unless FORESTG */
+    static size_t bytes(int max_nodes) { return kForestOff + (FORESTG ? 0 : (size_t)SPW * max_nodes * 4); }
 };
 
 NB_DEV void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -71,39 +76,46 @@ struct SubDecoder {
         while ((unsigned long long)(base + p) & 3ull) { ahead |= (u64)byte_at(p++) << (56 - 8 * navail); navail++; }
         rpos = p;
         wnext = word_at(rpos);
+        refill(); /* navail <= 3 here */
     }
-    /* keeps navail >= 4: a step shifts out at most 4 bytes */
-    NB_DEV void top_up() {
-        if (navail <= 4) { ahead |= (u64)wnext << (32 - 8 * navail); navail += 4; rpos += 4; wnext = word_at(rpos); }
-    }
-    /* decision with P(1) = p1 / 4096; the registers only move when `commit` */
+    /* merge the next word: navail <= 4 before, >= 4 after */
+    NB_DEV void refill() { ahead |= (u64)wnext << (32 - 8 * navail); navail += 4; rpos += 4; wnext = word_at(rpos); }
+    /* Decision with P(1) = p1 / 4096; the registers only move when `commit`.  navail >= 4 on entry (a step shifts out at
+     * most 4 bytes); about one step in forty needs the refill, so it is a real branch to an out-of-line body. */
     NB_DEV int step(u32 p1, bool commit) {
+        if (navail < 4) refill();
         const u32 mid = lo + split_point(hi - lo, p1);
         const int b = code <= mid;
-        if (commit) {
-            const u32 nlo = b ? lo : mid + 1, nhi = b ? mid : hi;
-            /* the reference shifts one byte at a time while the top bytes agree (R: NBLIC.c:563-572): that is the number of
-             * equal leading bytes, at most 4 (then lo = 0, hi = ~0 and the loop stops) */
-            const int sh = (__clz((int)(nlo ^ nhi)) >> 3) << 3;
-            lo = __funnelshift_lc(0u, nlo, sh);
-            hi = __funnelshift_lc(0xffffffffu, nhi, sh);
-            code = __funnelshift_lc((u32)(ahead >> 32), code, sh);
-            ahead <<= sh;
-            navail -= sh >> 3;
-        }
+        const u32 nlo = (commit && !b) ? mid + 1 : lo, nhi = (commit && b) ? mid : hi;
+        /* the reference shifts one byte at a time while the top bytes agree (R: NBLIC.c:563-572): that is the number of
+         * equal leading bytes, at most 4 (then lo = 0, hi = ~0 and the loop stops).  Without commit the registers are
+         * already normalised (top bytes differ) and the shift is 0. */
+        const int sh = (__clz((int)(nlo ^ nhi)) >> 3) << 3;
+        lo = __funnelshift_lc(0u, nlo, sh);
+        hi = __funnelshift_lc(0xffffffffu, nhi, sh);
+        code = __funnelshift_lc((u32)(ahead >> 32), code, sh);
+        ahead <<= sh;
+        navail -= sh >> 3;
         return b;
     }
 };
 
-NB_DEV int pick4(const int4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+/* learn_pair of coop_nblic.cuh with the stores left to the caller: the node of the main class after the decision, and
+ * the node of the side class (when both classes are the same node, the main result learns the second weight too and
+ * `cv2` is what has to be stored).  R: NBLIC.c:606-617,633-636 */
+NB_DEV void learn_two(u32 cu, u32 cv, u32 su, u32 sv, int wv, int bit, bool same, u32 &cu2, u32 &cv2) {
+    cu2 = learn_packed(cu, su, bit, N_MIX - wv);
+    const u32 src = same ? cu2 : cv, ssrc = same ? pair_sum(cu2) : sv;
+    cv2 = learn_packed(src, ssrc, bit, wv);
+}
 
 /*
  * Decode the pack of up to SPW streams `pack[0..SPW)` (task indices, -1 = empty; pack[0] >= 0; equal h x w).
- * smem: SubLayout<LPS, CTXG>; scratch: SPW x kSubScratchBytes of global memory private to this warp.
+ * smem: SubLayout<LPS, FORESTG>; scratch: SPW x kSubScratchBytes of global memory private to this warp.
  */
-template <int LPS, bool CTXG>
+template <int LPS, bool FORESTG>
 __device__ void subwarp_decode_pack(Task *tasks, const int *pack, uint8_t *smem, uint8_t *scratch, int max_nodes, int lane) {
-    using L = SubLayout<LPS, CTXG>;
+    using L = SubLayout<LPS, FORESTG>;
     constexpr int SPW = L::SPW;
     const int sl = lane % LPS, sid = lane / LPS;
     const int ti = pack[sid];
@@ -116,13 +128,16 @@ __device__ void subwarp_decode_pack(Task *tasks, const int *pack, uint8_t *smem,
 
     uint16_t *soft_tab = reinterpret_cast<uint16_t *>(smem + L::kSoftOff);
     uint16_t *fb = reinterpret_cast<uint16_t *>(smem + L::kFbaseOff) + sid * 16;
+    int *rk_count = reinterpret_cast<int *>(smem + L::kRankOff + sid * 112); /* the current key's 20 frequencies ...   */
+    uint8_t *rk_sym = reinterpret_cast<uint8_t *>(rk_count + N_RANKS);          /* ... and its rank -> symbol table        */
     PixRec *recs = reinterpret_cast<PixRec *>(smem + L::kRecOff);
-    int16_t *ctx_s = reinterpret_cast<int16_t *>(smem + L::kCtxOff) + sid * L::kCtxEntries;
-    u32 *forest = reinterpret_cast<u32 *>(smem + L::kForestOff) + (size_t)sid * max_nodes;
+    int16_t *ctx_s = reinterpret_cast<int16_t *>(smem + L::kCtxOff) + sid * 256;
     uint8_t *mine = scratch + (size_t)sid * kSubScratchBytes;
     int *count = reinterpret_cast<int *>(mine + kSubCountOff);
     uint8_t *rank = mine + kSubRankOff;
     int16_t *ctx_g = reinterpret_cast<int16_t *>(mine + kSubCtxOff);
+    u32 *forest = FORESTG ? reinterpret_cast<u32 *>(mine + kSubForestOff) : reinterpret_cast<u32 *>(smem + L::kForestOff) + (size_t)sid * max_nodes;
+    auto node = [&](int at) -> u32 { return FORESTG ? __ldcg(forest + at) : forest[at]; };
 
     const int top = (N_CLASSES - 1) / k_step, n_unary = 256 >> top;
     const u32 ktab = make_order_table(k_step);
@@ -135,17 +150,16 @@ __device__ void subwarp_decode_pack(Task *tasks, const int *pack, uint8_t *smem,
         for (int k = sl; k < n_nodes; k += LPS) forest[k] = (u32)N_MIX | ((u32)N_MIX << 16);
         if (sl == 0) { int b = 0; for (int u = 0; u < N_CLASSES; u++) { fb[u] = (uint16_t)b; b += (256 >> top) << (u / k_step); } }
         for (int d = lane; d <= 200; d += 32) { int u, v, wv; n_soft_class(d, u, v, wv); soft_tab[d] = (uint16_t)(u | (v << 4) | (wv << 8)); }
-        if (CTXG) { for (int k = sl; k < N_CTX_ENTRIES / 8; k += LPS) reinterpret_cast<int4 *>(ctx_g)[k] = make_int4(0, 0, 0, 0); }
-        else { for (int k = sl; k < N_CTX_ENTRIES; k += LPS) ctx_s[k] = 0; }
-        /* rank -> symbol tables: identity, 20 bytes per key = 5 words with period 5; frequencies 2 * (19 - rank) */
+        for (int k = sl; k < N_CTX_ENTRIES / 8; k += LPS) reinterpret_cast<int4 *>(ctx_g)[k] = make_int4(0, 0, 0, 0);
+        /* rank -> symbol tables: identity (5 words of a 32-byte row); frequencies 2 * (19 - rank), 5 x int4 per key */
+        for (int k = sl; k < 512 * kSubRankStride / 4; k += LPS) reinterpret_cast<u32 *>(rank)[k] = (k & 7) < 5 ? 0x03020100u + 0x04040404u * (u32)(k & 7) : 0u;
         for (int k = sl; k < N_RANK_ENTRIES / 4; k += LPS) {
             const int r = 4 * (k % 5);
-            reinterpret_cast<u32 *>(rank)[k] = 0x03020100u + 0x01010101u * (u32)r;
             reinterpret_cast<int4 *>(count)[k] = make_int4(38 - 2 * r, 36 - 2 * r, 34 - 2 * r, 32 - 2 * r);
         }
         __syncwarp();
     }
-    int cur_row = -1; /* class-pair row of the bias table held in ctx_s (CTXG) */
+    int cur_row = -1; /* class-pair row of the bias table held in ctx_s */
 
     SubDecoder dec;
     dec.start(t.slot, live ? t.slot_cap : 0u);
@@ -189,7 +203,11 @@ __device__ void subwarp_decode_pack(Task *tasks, const int *pack, uint8_t *smem,
                 int k = order_of(ktab, u);
                 if (order_of(ktab, v) != k) v = u;
                 int bu = fb[u], bv = fb[v];
-                if (CTXG) { /* bias-table row of this class pair: 512 bytes by cp.async behind the predictor */
+                /* first round's candidates = unary nodes 0..7 (slot = index << k): requested now, evaluated after the predictor */
+                int slot = (sl < 8 && sl < n_unary) ? (sl << k) : -1;
+                u32 cu = 0, cv = 0;
+                if (slot >= 0) { cu = node(bu + slot); cv = node(bv + slot); }
+                { /* bias-table row of this class pair: 512 bytes by cp.async behind the predictor */
                     const int want = u >> 1;
                     if (want != cur_row) {
                         const uint8_t *src = reinterpret_cast<const uint8_t *>(ctx_g + (want << 8));
@@ -203,28 +221,78 @@ __device__ void subwarp_decode_pack(Task *tasks, const int *pack, uint8_t *smem,
                 if (i >= 1) { const Pred pt = finish_predictor(nb, ra, rb); px0 = blend_prediction(pt, n_weight(pt.spread)); }
                 else { const Pred pt = predictor_terms(nb); px0 = blend_prediction(pt, n_weight(pt.spread)); }
                 const int tex = texture_bits(nb, px0);
-                int c;
-                if (CTXG) { cp_async_wait_all(); __syncwarp(); c = ctx_s[tex]; }
-                else c = ctx_s[((u >> 1) << 8) | tex];
+                cp_async_wait_all();
+                __syncwarp();
+                const int c = ctx_s[tex];
                 int px, sign;
                 n_bias_apply(c, px0, px, sign);
-                const int key = ((px << 1) | sign) * N_RANKS;
+                const int kidx = (px << 1) | sign, key = kidx * N_RANKS, rkey = kidx * kSubRankStride;
                 const int room = (int)(((u32)(min(px, 255 - px) + near) * qmagic) >> 16);
 
-                /* the key's rank table (20 bytes = 5 words) and frequencies (5 x int4) ride in sub-lanes 0..4; issued
-                 * before the symbol is decoded, used after */
-                u32 symw = 0;
-                int4 cnt = make_int4(0, 0, 0, 0);
-                if (sl < 5) {
-                    symw = __ldcg(reinterpret_cast<const u32 *>(rank + key) + sl);
-                    cnt = __ldcg(reinterpret_cast<const int4 *>(count + key) + sl);
-                }
+                /* the key's frequencies (5 x 16 bytes) and rank table (2 x 16 bytes) travel from L2 to the stream's staging
+                 * area by cp.async: requested before the symbol is decoded, waited for after */
+                if (sl < 5) cp_async16(reinterpret_cast<int4 *>(rk_count) + sl, reinterpret_cast<const int4 *>(count + key) + sl);
+                else if (sl < 7) cp_async16(rk_sym + 16 * (sl - 5), rank + rkey + 16 * (sl - 5));
 
                 /* ---- symbol: rounds of (evaluate <= 8 candidate nodes, walk them)  R: NBLIC.c:640-679 ---- */
                 int mode = 0 /* 0 unary run, 1 suffix, 2 done */, qbase = 0, z = 0, o_cur = 0, r_cur = 0, qz = 0;
                 for (;;) {
-                    int slot = -1; /* compacted slot of my candidate inside the class (coop_nblic.cuh: compact_node) */
-                    if (mode == 0) { /* unary nodes qbase .. qbase + 7: slot = index << k */
+                    u32 su = 2 * N_MIX, sv = 2 * N_MIX, p = 0;
+                    if (slot >= 0) { su = pair_sum(cu); sv = pair_sum(cv); p = mixed_p(cu, cv, su, sv, wv); }
+                    /* walk: unary = candidates 0, 1, 2 ... until a 0 decision; suffix = heap positions 0 -> 1 + b -> 3 + 2 b + b' */
+                    const int limit = mode == 0 ? min(8, n_unary - qbase) : min(3, r_cur);
+                    bool walking = mode < 2;
+                    int pos = 0, steps = 0;
+                    while (__any_sync(FULL, walking)) {
+                        const u32 pt = __shfl_sync(FULL, p, pos, LPS);
+                        const int b = dec.step(pt, walking);
+                        if (walking) {
+                            steps++;
+                            if (mode == 0) { pos += b; walking = b && pos < limit; }
+                            else { pos = 2 * pos + 1 + b; walking = steps < limit; }
+                        }
+                    }
+                    /* which candidates were consulted, and with which outcome */
+                    bool seen = false;
+                    int my_bit = 0;
+                    if (mode == 0) { seen = sl < steps; my_bit = sl < pos; } /* `pos` ones, then (if steps > pos) the closing 0 */
+                    else if (mode == 1) { /* heap node sl lies on the path iff it is an ancestor of the position reached */
+                        const int lvl = (sl >= 1) + (sl >= 3), up = steps - lvl;
+                        seen = up >= 1 && ((pos + 1) >> up) == sl + 1;
+                        my_bit = ((pos + 1) >> max(up - 1, 0)) & 1;
+                    }
+                    if (slot >= 0 && seen) {
+                        u32 cu2, cv2;
+                        const bool same = bu == bv;
+                        learn_two(cu, cv, su, sv, wv, my_bit, same, cu2, cv2);
+                        forest[bv + slot] = cv2;
+                        if (!same) forest[bu + slot] = cu2;
+                    }
+                    __syncwarp();
+                    if (mode == 0) {
+                        if (steps > pos) { /* a 0 closed the run at candidate pos */
+                            const int q = qbase + pos;
+                            z = q << k;
+                            if (k > 0) { mode = 1; o_cur = 1; r_cur = k; qz = q; } else mode = 2;
+                        } else {
+                            qbase += limit;
+                            if (qbase >= n_unary) { /* escape to the next order (R: NBLIC.c:658-662) */
+                                const int uu = (k + 1) * k_step;
+                                if (uu >= N_CLASSES) { corrupt = true; mode = 2; z = 0; } /* no encoder output gets here */
+                                else { k = k + 1; bu = bv = fb[uu]; qbase = n_unary >> 1; }
+                            }
+                        }
+                    } else if (mode == 1) { /* the `steps` bits taken, first one highest: pos + 1 = 1 b b' b'' in binary */
+                        const int bits = pos + 1 - (1 << steps);
+                        z += bits << (r_cur - steps);
+                        o_cur += (bits << (r_cur - steps)) + steps - __popc(bits); /* a 1 skips 2^(levels below) nodes, a 0 one */
+                        r_cur -= steps;
+                        if (r_cur == 0) mode = 2;
+                    }
+                    if (!__any_sync(FULL, mode < 2)) break;
+                    /* next round's candidates */
+                    slot = -1;
+                    if (mode == 0) { /* unary nodes qbase .. qbase + 7 */
                         if (sl < 8 && qbase + sl < n_unary) slot = (qbase + sl) << k;
                     } else if (mode == 1 && sl < 7) { /* heap position sl of the sub-tree rooted at pre-order offset o_cur, r_cur levels left */
                         const int lvl = (sl >= 1) + (sl >= 3);
@@ -235,66 +303,21 @@ __device__ void subwarp_decode_pack(Task *tasks, const int *pack, uint8_t *smem,
                             slot = (qz << k) + off;
                         }
                     }
-                    u32 cu = 0, cv = 0, su = 2 * N_MIX, sv = 2 * N_MIX, p = 0;
-                    if (slot >= 0) { cu = forest[bu + slot]; cv = forest[bv + slot]; su = pair_sum(cu); sv = pair_sum(cv); p = mixed_p(cu, cv, su, sv, wv); }
-
-                    const int ncand = min(8, n_unary - qbase);
-                    bool walking = mode < 2, zero = false;
-                    int pos = 0, steps = 0;
-                    u32 vis = 0, ones = 0; /* candidates consulted / consulted with outcome 1 */
-                    while (__any_sync(FULL, walking)) {
-                        dec.top_up();
-                        const u32 pt = __shfl_sync(FULL, p, pos, LPS);
-                        const int b = dec.step(pt, walking);
-                        if (walking) {
-                            vis |= 1u << pos; ones |= (u32)b << pos;
-                            if (mode == 0) {
-                                if (b) { pos++; walking = pos < ncand; } else { zero = true; walking = false; }
-                            } else {
-                                o_cur += b ? (1 << (r_cur - 1)) : 1;
-                                r_cur--;
-                                z += b << r_cur;
-                                pos = 2 * pos + 1 + b;
-                                steps++;
-                                walking = steps < 3 && r_cur > 0;
-                            }
-                        }
-                    }
-                    if (slot >= 0 && ((vis >> sl) & 1u)) learn_pair(forest, bu + slot, bv + slot, cu, cv, su, sv, wv, (int)((ones >> sl) & 1u));
-                    __syncwarp();
-                    if (mode == 0) {
-                        if (zero) {
-                            const int q = qbase + pos;
-                            z = q << k;
-                            if (k > 0) { mode = 1; o_cur = 1; r_cur = k; qz = q; } else mode = 2;
-                        } else {
-                            qbase += ncand;
-                            if (qbase >= n_unary) { /* escape to the next order (R: NBLIC.c:658-662) */
-                                const int uu = (k + 1) * k_step;
-                                if (uu >= N_CLASSES) { corrupt = true; mode = 2; z = 0; } /* no encoder output gets here */
-                                else { k = k + 1; bu = bv = fb[uu]; qbase = n_unary >> 1; }
-                            }
-                        }
-                    } else if (mode == 1 && r_cur == 0) mode = 2;
-                    if (!__any_sync(FULL, mode < 2)) break;
+                    if (slot >= 0) { cu = node(bu + slot); cv = node(bv + slot); }
                 }
 
                 /* ---- rank mapper, decoder direction (R: NBLIC.c:470-523) ---- */
+                cp_async_wait_all();
+                __syncwarp();
                 int y = z;
-                {
-                    const int zc = min(z, N_RANKS - 1), zp = max(zc - 1, 0);
-                    const u32 wz = __shfl_sync(FULL, symw, zc >> 2, LPS), wp = __shfl_sync(FULL, symw, zp >> 2, LPS);
-                    const int cz = __shfl_sync(FULL, pick4(cnt, zc & 3), zc >> 2, LPS) + 1;
-                    const int cp = __shfl_sync(FULL, pick4(cnt, zp & 3), zp >> 2, LPS);
-                    if (z < N_RANKS) {
-                        y = (int)((wz >> (8 * (zc & 3))) & 255u);
-                        if (sl == 0) {
-                            if (z > 0 && cp < cz) { /* one adjacent promotion */
-                                const int other = (int)((wp >> (8 * (zp & 3))) & 255u);
-                                count[key + z] = cp; count[key + z - 1] = cz;
-                                rank[key + z] = (uint8_t)other; rank[key + z - 1] = (uint8_t)y;
-                            } else count[key + z] = cz;
-                        }
+                if (z < N_RANKS) {
+                    y = rk_sym[z];
+                    if (sl == 0) {
+                        const int cz = rk_count[z] + 1;
+                        if (z > 0 && rk_count[z - 1] < cz) { /* one adjacent promotion */
+                            count[key + z] = rk_count[z - 1]; count[key + z - 1] = cz;
+                            rank[rkey + z] = rk_sym[z - 1]; rank[rkey + z - 1] = (uint8_t)y;
+                        } else count[key + z] = cz;
                     }
                 }
 
@@ -307,10 +330,8 @@ __device__ void subwarp_decode_pack(Task *tasks, const int *pack, uint8_t *smem,
                 const int x = clampi(up ? px + mag : px - mag, 0, 255);
                 if (sl == jj) my_x = (u32)x;
                 err = clampi(x - px0, -127, 127);
-                const int c_new = n_bias_learn(c, err);
-                if (CTXG) { /* write through; the lane that fetches an entry's 16-byte piece also stores it (same-thread order) */
-                    if (sl == ((tex >> 3) % LPS)) { ctx_s[tex] = (int16_t)c_new; ctx_g[(cur_row << 8) | tex] = (int16_t)c_new; }
-                } else if (sl == 0) ctx_s[((u >> 1) << 8) | tex] = (int16_t)c_new;
+                /* write through; the lane that fetches an entry's 16-byte piece also stores it (same-thread order) */
+                if (sl == ((tex >> 3) % LPS)) { const int c_new = n_bias_learn(c, err); ctx_s[tex] = (int16_t)c_new; ctx_g[(cur_row << 8) | tex] = (int16_t)c_new; }
                 x2 = x1; x1 = x;
                 __syncwarp();
             }

@@ -8,15 +8,15 @@ import torch
 from nblic_image_compression_b200 import api
 from nblic_image_compression_b200.synth import gen
 
-VARIANTS = [("32", None), ("16", None), ("8", None), ("16", "1"), ("8", "1")]
+VARIANTS = [("32", None), ("8", None), ("8", "1")]
 
 
 def make_codec(lps, ctx_smem):
     os.environ["NBLIC_B200_LPS"] = lps
     if ctx_smem:
-        os.environ["NBLIC_B200_CTX_SMEM"] = ctx_smem
+        os.environ["NBLIC_B200_FOREST_SMEM"] = ctx_smem
     else:
-        os.environ.pop("NBLIC_B200_CTX_SMEM", None)
+        os.environ.pop("NBLIC_B200_FOREST_SMEM", None)
     return api.Codec(0)
 
 
@@ -45,9 +45,9 @@ def correctness():
                 k = bad[0]
                 d = out[k]
                 where = None if d is None else np.argwhere(d[0] != want[k])[:3].tolist()
-                print(f"MISMATCH near={near} lps={lps} ctx_smem={cs}: images {bad[:10]} shape {imgs[k].shape} first diffs {where} status {c.last_status[k]}", flush=True)
+                print(f"MISMATCH near={near} lps={lps} forest_smem={cs}: images {bad[:10]} shape {imgs[k].shape} first diffs {where} status {c.last_status[k]}", flush=True)
             else:
-                print(f"ok near={near} lps={lps} ctx_smem={cs} ({len(imgs)} images, mapping {c.last_mapping})", flush=True)
+                print(f"ok near={near} lps={lps} forest_smem={cs} ({len(imgs)} images, mapping {c.last_mapping})", flush=True)
             c.close()
         # corrupt payloads must not fault
         bad_streams = [s[:16] + bytes(rng.integers(0, 256, size=len(s) - 16, dtype=np.uint8)) for s in streams[:12]] + [s[: 16 + (len(s) - 16) // 2] for s in streams[:12]]
@@ -81,7 +81,7 @@ def timing(n, h, w):
             assert rc == 0
             best = min(best, c.last_coder_ms)
         same = torch.equal(d_dec, d_pix)
-        print(f"decode lps={lps} ctx_smem={cs}: {best:.1f} ms ({n * npx / best / 1e3:.0f} MPix/s) slots {c.last_slots} exact={same}", flush=True)
+        print(f"decode lps={lps} forest_smem={cs}: {best:.1f} ms ({n * npx / best / 1e3:.0f} MPix/s) slots {c.last_slots} exact={same}", flush=True)
         c.close()
 
 
