@@ -214,6 +214,79 @@ def profile_figures(kernel_key):
     return k, "ncu --set full capture of this build (git %s, shape %s)" % (rec.get("git_head", "?")[:12], k.get("shape"))
 
 
+def _cpu_one_core(img, near, effort):
+    """(encode ms, decode ms, stream bytes) of the CPU codec on one core for one image (reference build when present)."""
+    path, kind = _cpu_lib()
+    lib = C.CDLL(path)
+    u8p, u16p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.POINTER(C.c_int)
+    h, w = img.shape
+    src = img.copy()
+    out = np.zeros(2 * h * w + 65536, dtype=np.uint8)
+    dec = np.zeros(h * w, dtype=np.uint8)
+    n_, e_, hh, ww = C.c_int(near), C.c_int(effort), C.c_int(), C.c_int()
+    t0 = time.perf_counter()
+    if kind == "reference":
+        if effort == 0:
+            n = 2 * lib.QNBLICcompress(out.ctypes.data_as(u16p), src.ctypes.data_as(u8p), h, w)
+        else:
+            n = lib.NBLICcompress(0, out.ctypes.data_as(u8p), src.ctypes.data_as(u8p), h, w, C.byref(n_), C.byref(e_))
+        t1 = time.perf_counter()
+        if effort == 0:
+            rc = lib.QNBLICdecompress(out.ctypes.data_as(u16p), dec.ctypes.data_as(u8p), C.byref(hh), C.byref(ww))
+        else:
+            rc = lib.NBLICdecompress(0, out.ctypes.data_as(u8p), dec.ctypes.data_as(u8p), C.byref(hh), C.byref(ww), C.byref(n_), C.byref(e_))
+    else:
+        lib.oracle_n_decode.argtypes = [u8p, C.c_long, u8p, ip, ip, ip, ip]
+        lib.oracle_q_decode.argtypes = [u16p, C.c_long, u8p, ip, ip]
+        if effort == 0:
+            n = 2 * lib.oracle_q_encode(src.ctypes.data_as(u8p), h, w, out.ctypes.data_as(u16p))
+        else:
+            n = lib.oracle_n_encode(src.ctypes.data_as(u8p), h, w, C.byref(n_), C.byref(e_), out.ctypes.data_as(u8p))
+        t1 = time.perf_counter()
+        if effort == 0:
+            rc = lib.oracle_q_decode(out.ctypes.data_as(u16p), n // 2, dec.ctypes.data_as(u8p), C.byref(hh), C.byref(ww))
+        else:
+            rc = lib.oracle_n_decode(out.ctypes.data_as(u8p), n, dec.ctypes.data_as(u8p), C.byref(hh), C.byref(ww), C.byref(n_), C.byref(e_))
+    t2 = time.perf_counter()
+    assert n > 0 and rc == 0 and np.array_equal(dec.reshape(h, w), img)
+    return 1e3 * (t1 - t0), 1e3 * (t2 - t1), int(n), bytes(out[:n]), kind
+
+
+def latency_records(codec, api, cores):
+    """Few-stream configs through the host-buffer API (best of 3 wall-clock calls after one warm-up), with the CPU
+    codec on ONE core beside them; every GPU stream is compared byte for byte with the CPU's."""
+    from nblic_image_compression_b200.synth import gen
+    out = {}
+    try:
+        gold = os.path.join(ROOT, "tests", "golden", "kodak_e1n0")
+        names = sorted(f for f in os.listdir(gold) if f.endswith(".nblic"))
+        kodak = [d[0] for d in codec.decode_batch([open(os.path.join(gold, f), "rb").read() for f in names])]
+        cases = [("configs[0]: Kodak 01, -n0 -e0", [kodak[0]], 0), ("configs[1]: 24 Kodak images, -n0 -e1", kodak, 1),
+                 ("Kodak 01, -n0 -e1", [kodak[0]], 1), ("one synthetic 4096x4096 image, -n0 -e1", [gen(4096, 4096, 0)], 1)]
+        for label, imgs, effort in cases:
+            px = sum(im.size for im in imgs)
+            enc_ms, dec_ms = [], []
+            for it in range(4):
+                t0 = time.perf_counter()
+                streams, _, st = codec.encode_batch(imgs, 0, effort)
+                t1 = time.perf_counter()
+                mapping = codec.last_mapping
+                dec = codec.decode_batch(streams)
+                t2 = time.perf_counter()
+                if it:
+                    enc_ms.append(1e3 * (t1 - t0)); dec_ms.append(1e3 * (t2 - t1))
+            assert all(np.array_equal(d[0], im) for d, im in zip(dec, imgs))
+            ce, cd, cn, cbytes, kind = _cpu_one_core(imgs[0], 0, effort)
+            rec = {"images": len(imgs), "mpixel": round(px / 1e6, 3), "encode_ms": round(min(enc_ms), 3), "decode_ms": round(min(dec_ms), 3),
+                   "encode_mpix_s": round(px / min(enc_ms) / 1e3, 2), "decode_mpix_s": round(px / min(dec_ms) / 1e3, 2), "encode_mapping": mapping,
+                   "cpu_one_core_first_image": {"encode_ms": round(ce, 2), "decode_ms": round(cd, 2), "kind": kind},
+                   "first_stream_equals_cpu": streams[0] == cbytes, "timing": "host wall clock around the host-buffer calls (pageable numpy buffers), best of 3"}
+            out[label] = rec
+    except Exception as ex:  # pragma: no cover
+        out["error"] = repr(ex)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -462,6 +535,12 @@ def main():
                 rec["e2e"] = round(2 * px / r["e2e_s"] / 1e6, 3)
             per_effort[f"e{effort}n{near}"] = rec
 
+    # ---- latency configs (configs[0], configs[1], and a single 4096 x 4096 image): few streams, so the lossless encoders
+    # run as whole-GPU pipelines (pipe_qnblic.cuh / pipe_nblic.cuh); a decoder is one serial chain per image ----
+    latency = None
+    if rank == 0 and world == 1 and args.per_effort_images > 0:
+        latency = latency_records(codec, api, cores)
+
     # ---- strong scaling of configs[4] as named: B images in total over the ranks ------------------------
     strong = None
     if world > 1:
@@ -497,7 +576,8 @@ def main():
             "config": {"workload": workload, "mapping": main_r["mapping"], "l2": "inputs larger than L2 (batch pixels >> 126 MB)",
                        "encode_mpix_s": round(world * B * npx / enc_s / 1e6, 3), "decode_mpix_s": round(world * B * npx / dec_s / 1e6, 3),
                        "bits_per_pixel": round(8.0 * main_r["stream_bytes"] / (B * npx), 4), "parity": parity,
-                       "resident_slots": {"encode": main_r["enc_slots"], "decode": main_r["dec_slots"]}, "per_effort": per_effort},
+                       "resident_slots": {"encode": main_r["enc_slots"], "decode": main_r["dec_slots"]}, "per_effort": per_effort,
+                       "latency": latency},
             "e2e": e2e_rec, "gpu_launches": int(main_r["launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         if strong:

@@ -84,6 +84,16 @@ enum {
 };
 int nblic_b200_set_mapping(nblic_b200_ctx *ctx, int mapping);
 
+/* Single-image pipelines: a lossless effort-0 / effort-1 ENCODE of a small batch spreads every
+ * stage but the entropy coder over the whole GPU (csrc/pipe_qnblic.cuh, csrc/pipe_nblic.cuh) instead of giving each
+ * image one warp -- the bit-exact form of the reference's -t option (src/QNBLIC.c:660-866).  Same bytes either way. */
+enum {
+    NBLIC_B200_PIPE_AUTO = -1,  /* by batch size: small batches are pipelined (default) */
+    NBLIC_B200_PIPE_NEVER = 0,
+    NBLIC_B200_PIPE_ALWAYS = 1
+};
+int nblic_b200_set_pipeline(nblic_b200_ctx *ctx, int mode);
+
 /* Per-image result codes written to `status` (may be NULL). */
 enum {
     NBLIC_B200_OK = 0,
@@ -115,6 +125,13 @@ int nblic_b200_encode_batch(nblic_b200_ctx *ctx, int n, const uint8_t *const *im
 int nblic_b200_decode_batch(nblic_b200_ctx *ctx, int n, const uint8_t *const *streams, const size_t *stream_lens,
                             uint8_t *const *images, const size_t *img_caps, int *heights, int *widths,
                             int *nears, int *efforts, int *status);
+
+/* Page-locked (pinned) host memory for the host-buffer calls above: copies from / to such buffers are asynchronous
+ * DMA transfers that overlap the coder kernels (pageable buffers work too, through the driver's staging).  What the
+ * reference's FileIO.c buffers (src/NBLIC_main.c:141: static 200 MB arrays) become in a pipelined caller
+ * (csrc/nblic_batch_cli.c).  NULL on failure; a CUDA device must be usable. */
+void *nblic_b200_host_alloc(size_t bytes);
+void nblic_b200_host_free(void *p);
 
 /* Parse a stream header on the host (no CUDA).  Returns 0 and fills the outputs, or -1.
  * effort 0 = "Q0.2".  Follows src/NBLIC.c:698-745 and src/QNBLIC.c:475-486. */

@@ -21,6 +21,7 @@ _u64p = C.POINTER(C.c_uint64)
 _pp = C.POINTER(C.c_void_p)
 
 MAP_AUTO, MAP_WARP, MAP_LANE = 0, 1, 2
+PIPE_AUTO, PIPE_NEVER, PIPE_ALWAYS = -1, 0, 1
 OK, BAD_DIMS, BAD_HEADER, OVERFLOW, CORRUPT = 0, 1, 2, 3, 4
 
 SYMBOLS = [
@@ -28,8 +29,8 @@ SYMBOLS = [
     "NBLICcompress", "NBLICdecompress", "QNBLICcompress", "QNBLICcompressMultiThread", "QNBLICdecompress",
     "nblic_b200_hint_input_len", "nblic_b200_stream_bound",
     # batch layer
-    "nblic_b200_create", "nblic_b200_destroy", "nblic_b200_last_error", "nblic_b200_set_mapping",
-    "nblic_b200_encode_batch", "nblic_b200_decode_batch", "nblic_b200_peek",
+    "nblic_b200_create", "nblic_b200_destroy", "nblic_b200_last_error", "nblic_b200_set_mapping", "nblic_b200_set_pipeline",
+    "nblic_b200_encode_batch", "nblic_b200_decode_batch", "nblic_b200_peek", "nblic_b200_host_alloc", "nblic_b200_host_free",
     "nblic_b200_encode_batch_device", "nblic_b200_decode_batch_device", "nblic_b200_synth_gray", "nblic_b200_synth_gray_batch", "nblic_b200_debug_divcheck",
     "nblic_b200_launch_count", "nblic_b200_last_coder_ms", "nblic_b200_last_slots", "nblic_b200_last_mapping", "nblic_b200_stream_handle", "nblic_b200_version",
 ]
@@ -52,6 +53,7 @@ def load_library() -> C.CDLL:
     lib.nblic_b200_last_error.restype = C.c_char_p
     lib.nblic_b200_last_error.argtypes = [C.c_void_p]
     lib.nblic_b200_set_mapping.argtypes = [C.c_void_p, C.c_int]
+    lib.nblic_b200_set_pipeline.argtypes = [C.c_void_p, C.c_int]
     lib.nblic_b200_stream_bound.restype = C.c_size_t
     lib.nblic_b200_stream_bound.argtypes = [C.c_int, C.c_int]
     lib.nblic_b200_hint_input_len.argtypes = [C.c_size_t]
@@ -128,6 +130,11 @@ class Codec:
     def set_mapping(self, mapping: int):
         if self.lib.nblic_b200_set_mapping(self.ctx, mapping) != 0:
             raise ValueError("bad mapping")
+
+    def set_pipeline(self, mode: int):
+        """PIPE_AUTO (-1) / PIPE_NEVER (0) / PIPE_ALWAYS (1): whole-GPU single-image encode of lossless effort 0 / 1."""
+        if self.lib.nblic_b200_set_pipeline(self.ctx, mode) != 0:
+            raise ValueError("bad pipeline mode")
 
     @property
     def launches(self) -> int:

@@ -56,7 +56,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
     subprocess.run([_nvcc(), "-shared", "-o", LIB, *objs, "-lpthread", "-cudart", "shared"], check=True)
     subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-std=gnu99", "-o", CLI, os.path.join(CSRC, "nblic_batch_cli.c"),
-                    "-L" + HERE, "-lnblic_b200", "-Wl,-rpath,$ORIGIN"], check=True)
+                    "-L" + HERE, "-lnblic_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
 
 

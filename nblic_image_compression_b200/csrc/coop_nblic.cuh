@@ -28,6 +28,7 @@
 #pragma once
 #include "codec_core.cuh"
 #include "coop_avp.cuh"
+#include "row_stage.cuh"
 
 namespace nblic {
 
@@ -44,23 +45,10 @@ struct __align__(16) PixRec {
     u32 orig;   /* encoder: the original pixel                                                */
 };
 
-/* Phase P of the feedback modes for pixel (i, j), i >= 1: neighbours of the two rows above with the
- * reference's border fallbacks (R: NBLIC.c:288-303) and the a-free partial sums. */
-NB_DEV PixRec make_pixrec(const uint8_t *row, int w, int i, int j, u32 orig) {
+/* The record of a pixel from its ten neighbours of the two rows above (a-free partial sums of the directional costs). */
+NB_DEV PixRec pixrec_from(int b, int c, int d, int f, int g, int hh, int q, int r, int s, int t, u32 orig) {
     PixRec pr;
     pr.orig = orig;
-    const uint8_t *r1 = row - w, *r2 = r1 - w;
-    const bool up2 = i >= 2, l1 = j >= 1, l2 = j >= 2, rt1 = j + 1 < w, rt2 = j + 2 < w;
-    const int b = r1[j];
-    const int c = l1 ? (int)r1[j - 1] : b;
-    const int d = rt1 ? (int)r1[j + 1] : b;
-    const int f = up2 ? (int)r2[j] : b;
-    const int g = (up2 && rt1) ? (int)r2[j + 1] : f;
-    const int hh = (up2 && l1) ? (int)r2[j - 1] : f;
-    const int q = l2 ? (int)r1[j - 2] : c;
-    const int r = (up2 && rt2) ? (int)r2[j + 2] : g;
-    const int s = (up2 && l2) ? (int)r2[j - 2] : hh;
-    const int t = rt2 ? (int)r1[j + 2] : d;
     pr.bcdf = (u32)b | ((u32)c << 8) | ((u32)d << 16) | ((u32)f << 24);
     pr.ghqr = (u32)g | ((u32)hh << 8) | ((u32)q << 16) | ((u32)r << 24);
     const int act = abs(b - c) + abs(b - d) + abs(b - f) + abs(d - g);
@@ -75,6 +63,28 @@ NB_DEV PixRec make_pixrec(const uint8_t *row, int w, int i, int j, u32 orig) {
     pr.k01 = (u32)K0 | ((u32)K1 << 16); pr.k23 = (u32)K2 | ((u32)K3 << 16); pr.k45 = (u32)K4 | ((u32)K5 << 16);
     pr.k6_lin = (u32)K6 | ((u32)(9 * b + 2 * d - 2 * c - f + 1024) << 16);
     return pr;
+}
+/* Phase P of the feedback modes for pixel (i, j), i >= 1: neighbours of the two rows above with the
+ * reference's border fallbacks (R: NBLIC.c:288-303), read from global memory (row 1, where f..s fall back per column). */
+NB_DEV PixRec make_pixrec(const uint8_t *row, int w, int i, int j, u32 orig) {
+    const uint8_t *r1 = row - w, *r2 = r1 - w;
+    const bool up2 = i >= 2, l1 = j >= 1, l2 = j >= 2, rt1 = j + 1 < w, rt2 = j + 2 < w;
+    const int b = r1[j];
+    const int c = l1 ? (int)r1[j - 1] : b;
+    const int d = rt1 ? (int)r1[j + 1] : b;
+    const int f = up2 ? (int)r2[j] : b;
+    const int g = (up2 && rt1) ? (int)r2[j + 1] : f;
+    const int hh = (up2 && l1) ? (int)r2[j - 1] : f;
+    const int q = l2 ? (int)r1[j - 2] : c;
+    const int r = (up2 && rt2) ? (int)r2[j + 2] : g;
+    const int s = (up2 && l2) ? (int)r2[j - 2] : hh;
+    const int t = rt2 ? (int)r1[j + 2] : d;
+    return pixrec_from(b, c, d, f, g, hh, q, r, s, t, orig);
+}
+/* The same from rows staged in shared memory with materialised halo cells (row_stage.cuh), i >= 2: no predicates.
+ * p1 / p2 -> pixel j of rows i-1 / i-2. */
+NB_DEV PixRec make_pixrec_staged(const uint8_t *p1, const uint8_t *p2, u32 orig) {
+    return pixrec_from(p1[0], p1[-1], p1[1], p2[0], p2[1], p2[-1], p1[-2], p2[2], p2[-2], p1[2], orig);
 }
 /* Finish the 7-direction predictor from a record (words ra, rb) once a and e are known.  nb must already
  * hold a, b, c, d, e, q.  R: NBLIC.c:307-364 / QNBLIC.c:94-143 */
@@ -107,7 +117,7 @@ struct CoopSmem {
     uint16_t fbase[N_CLASSES];         /* first forest slot of class u                                 */
 };
 /* Dynamic shared memory of a coop_nblic_kernel CTA, in this order:
- *   CoopSmem | PixRec[32] (feedback modes) | AvpSmem (efforts 2/3) | rank[512*20] bytes (effort 1) | forest[]
+ *   CoopSmem | PixRec[32] (feedback modes) | staged row tiles (row_stage.cuh) | AvpSmem (efforts 2/3) | rank[512*20] bytes (effort 1) | forest[]
  * The rank tables (10 KB: encoder symbol -> rank, decoder rank -> symbol) stay in shared memory for
  * effort 1 while the batch fits the 11 streams/SM that allows; efforts 2/3 spend ~40k cycles per pixel in
  * the least-squares solve, so there (and for effort-1 batches larger than 11 x SMs images, RG = true) the
@@ -115,8 +125,10 @@ struct CoopSmem {
 template <int NAVP, int MODE, bool RG> struct CoopLayout {
     static constexpr bool kFeedback = MODE != 0;
     static constexpr bool kRankGlobal = RG;
+    static constexpr int kStageRows = kFeedback ? 2 : 3; /* row_stage.cuh: the rows above (+ the current row when all pixels are known) */
     static constexpr size_t kRecOff = (sizeof(CoopSmem) + 15) & ~(size_t)15;
-    static constexpr size_t kAvpOff = kRecOff + (kFeedback ? sizeof(PixRec) * 32 : 0);
+    static constexpr size_t kStageOff = kRecOff + (kFeedback ? sizeof(PixRec) * 32 : 0);
+    static constexpr size_t kAvpOff = kStageOff + 2 * kStageRows * kStageLine;
     static constexpr size_t kRankOff = kAvpOff + (NAVP > 0 ? sizeof(AvpSmem) : 0);
     static constexpr size_t kForestOff = (kRankOff + (kRankGlobal ? 0 : N_RANK_ENTRIES) + 15) & ~(size_t)15;
 };
@@ -448,8 +460,8 @@ NB_DEV int coop_rank_decode(uint8_t *rank, int *count, int key, int z, int lane,
  * `stream` must be 128-byte aligned.  Returns the stream length or 0xffffffff on overflow.
  */
 template <bool RG>
-__device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, uint8_t *rank, u32 *forest,
-                                        int *count, int lane) {
+__device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t *stream, u32 cap, CoopSmem &sm, uint8_t *stage_buf, uint8_t *rank,
+                                        u32 *forest, int *count, int lane) {
     const int k_step = 3, top = (N_CLASSES - 1) / k_step; /* near = 0 (R: NBLIC.c:769) */
     const u32 ktab = make_order_table(k_step);
     coop_reset(sm, rank, forest, k_step, count, lane);
@@ -457,6 +469,8 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
     rc.out.start(stream, cap, lane);
     coop_put_header(rc, h, w, 0, k_step, 1);
     rc.start();
+    RowStage<3> rows;
+    rows.start(stage_buf, img, h, w);
 
     for (int i = 0; i < h; i++) {
         int carry_px0 = 0; /* px0 of the pixel left of this block */
@@ -465,10 +479,20 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
             const bool active = j0 + lane < w;
             const int j = min(j0 + lane, w - 1);
             Nb nb;
-            sample_positional(img, w, i, j, nb);
+            int x;
+            if (i >= 2) { /* rows i, i-1, i-2 come from shared memory, staged by cp.async one 64-pixel tile ahead */
+                if ((j0 & (kStageTile - 1)) == 0) {
+                    const bool more = j0 + kStageTile < w;
+                    rows.advance(i, j0, more ? i : (i + 1 < h ? i + 1 : -1), more ? j0 + kStageTile : 0, lane, 32, lane == 0);
+                }
+                sample_staged3(rows, j - (j0 & ~(kStageTile - 1)), nb, x);
+                if (j == 1) nb.e = nb.a;
+            } else {
+                sample_positional(img, w, i, j, nb);
+                x = img[(size_t)i * w + j];
+            }
             const Pred pt = predictor_terms(nb);
             const int px0 = blend_prediction(pt, n_weight(pt.spread));
-            const int x = img[(size_t)i * w + j];
             int px0_left = __shfl_up_sync(FULL, px0, 1);
             if (lane == 0) px0_left = carry_px0;
             const int err_in = j == 0 ? 0 : clampi(nb.a - px0_left, -127, 127); /* nb.a is the coded value of pixel j-1 */
@@ -618,8 +642,8 @@ __device__ u32 coop_e1_encode_lossless(const uint8_t *img, int h, int w, uint8_t
  */
 template <int NAVP, bool DEC, bool RG>
 __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *out_rec, int h, int w, int near, int k_step, uint8_t *stream,
-                             u32 cap, CoopSmem &sm, PixRec *recs, AvpSmem *avp_sm, uint8_t *rank, u32 *forest, i64 *Brow, i64 *Frow, int *count,
-                             int lane) {
+                             u32 cap, CoopSmem &sm, PixRec *recs, uint8_t *stage_buf, AvpSmem *avp_sm, uint8_t *rank, u32 *forest, i64 *Brow, i64 *Frow,
+                             int *count, int lane) {
     constexpr int AN = NAVP > 0 ? NAVP : 1;
     constexpr int AM = AvpGeom<AN>::M, ANS = AvpGeom<AN>::NS;
     const int top = (N_CLASSES - 1) / k_step;
@@ -636,6 +660,8 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
     if constexpr (DEC) { rc.in.start(stream, cap, 16, lane); }
     else { rc.out.start(stream, cap, lane); coop_put_header(rc, h, w, near, k_step, NAVP == 0 ? 1 : (NAVP == 6 ? 2 : 3)); }
     rc.start();
+    RowStage<2> rows; /* rows i-1, i-2 of the raster the neighbours come from (for a decoder: what it wrote itself) */
+    rows.start(stage_buf, nbimg, h, w);
 
     for (int i = 0; i < h; i++) {
         int err = 0, x1 = 0, x2 = 0; /* previous two pixels of this row */
@@ -647,7 +673,11 @@ __device__ u32 coop_feedback(const uint8_t *src, const uint8_t *nbimg, uint8_t *
                 const int j = min(j0 + lane, w - 1);
                 PixRec pr;
                 const u32 orig = DEC ? 0u : (u32)src[(size_t)i * w + j];
-                if (i >= 1) pr = make_pixrec(row, w, i, j, orig);
+                if (i >= 2) { /* the tile after this one (same row: the next row's neighbours are not all written yet) is prefetched */
+                    if ((j0 & (kStageTile - 1)) == 0) rows.advance(i, j0, j0 + kStageTile < w ? i : -1, j0 + kStageTile, lane, 32, lane == 0);
+                    const int jr = j - (j0 & ~(kStageTile - 1));
+                    pr = make_pixrec_staged(rows.at(0, jr), rows.at(1, jr), orig);
+                } else if (i == 1) pr = make_pixrec(row, w, i, j, orig);
                 else { pr.bcdf = pr.ghqr = pr.st_act = pr.k01 = pr.k23 = pr.k45 = pr.k6_lin = 0; pr.orig = orig; }
                 recs[lane] = pr;
                 __syncwarp();

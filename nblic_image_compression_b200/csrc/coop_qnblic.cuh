@@ -27,12 +27,14 @@ struct QCoopSmem { /* encoder: only the bias table is latency critical; the 12 x
                      * live in global memory / L2 -- pass 1 adds to them with fire-and-forget atomics, pass 2 fetches 32
                      * symbols' entries one block ahead -- which doubles the resident streams per SM (17 instead of 8) */
     int ctx[Q_CTX_ENTRIES]; /* 12 KB bias-cancel table */
+    __align__(16) uint8_t stage[RowStage<3, 32>::kBytes]; /* rows i, i-1, i-2: cp.async tiles of 32 pixels (row_stage.cuh); 384 B keeps 17 streams per SM */
 };
 enum { Q_CUM_STRIDE = 258 }; /* 257 cumulative frequencies per class (freq = difference), padded to 4 bytes */
 struct QDecSmem { /* decoder: 19.2 KB instead of 25 KB, 11 instead of 8 resident streams per SM */
     int ctx[Q_CTX_ENTRIES];                 /* 12 KB bias-cancel table                            */
     uint16_t cum[Q_CLASSES * Q_CUM_STRIDE]; /*  6 KB cumulative frequencies, cum[256] = 2^15      */
     PixRec rec[32];                         /*  1 KB phase-P records (and scratch while the histograms are parsed) */
+    __align__(16) uint8_t stage[2 * 2 * kStageLine]; /* rows i-1, i-2: cp.async tiles (row_stage.cuh) */
 };
 
 /* rows 0 and 1 (and any row of a sequential fallback): the reference loop, warp-uniform, leader stores */
@@ -85,6 +87,8 @@ __device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u
     uint16_t *sym = reinterpret_cast<uint16_t *>(sym8); /* cls | y << 8 per pixel, raster order */
     for (int k = lane; k < Q_CTX_ENTRIES; k += 32) { sm.ctx[k] = 0; tab[k] = 0; }
     __syncwarp();
+    RowStage<3, 32> rows;
+    rows.start(sm.stage, img, h, w);
 
     for (int i = 0; i < h; i++) { /* pass 1: model every pixel.  R: QNBLIC.c:586-623 */
         const uint8_t *row = img + (size_t)i * w;
@@ -101,15 +105,20 @@ __device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u
         for (int j0 = 0; j0 < w; j0 += 32) {
             const bool active = j0 + lane < w;
             const int j = min(j0 + lane, w - 1);
+            /* rows i, i-1, i-2 from shared memory, staged by cp.async one 32-pixel tile ahead.  At column 1 QNBLIC's shift
+             * register still holds the old a = img[i-1][0] in e: exactly the halo cell r0[-1], so no lane is patched. */
+            {
+                const bool more = j0 + 32 < w;
+                rows.advance(i, j0, more ? i : (i + 1 < h ? i + 1 : -1), more ? j0 + 32 : 0, lane, 32, lane == 0);
+            }
             Nb nb;
-            sample_positional(img, w, i, j, nb);
-            if (j == 1) nb.e = row[-w]; /* the shift register still holds the old a = img[i-1][0] */
+            int x;
+            sample_staged3(rows, j - j0, nb, x);
             const Pred pt = predictor_terms(nb);
             const int px0 = blend_prediction(pt, q_weight(pt.spread));
-            const int x = row[j];
             int px0_left = __shfl_up_sync(FULL, px0, 1);
             if (lane == 0) px0_left = carry_px0;
-            const int err_in = j == 0 ? 0 : (int)row[j - 1] - px0_left;
+            const int err_in = j == 0 ? 0 : nb.a - px0_left;
             const int cls = q_class(activity(nb, err_in));
             const int adr = active ? q_ctx_address(nb, px0, cls) : 0x10000 + lane;
             carry_px0 = __shfl_sync(FULL, px0, 31);
@@ -257,6 +266,8 @@ __device__ void coop_q_decode(const uint16_t *in, u32 avail, uint8_t *img, int h
         return y;
     };
 
+    RowStage<2> rows; /* rows i-1, i-2 of the decoder's own output */
+    rows.start(sm.stage, img, h, w);
     for (int i = 0; i < h; i++) { /* R: QNBLIC.c:520-552 */
         uint8_t *row = img + (size_t)i * w;
         if (i < 2) {
@@ -270,7 +281,11 @@ __device__ void coop_q_decode(const uint16_t *in, u32 avail, uint8_t *img, int h
         }
         int err = 0, x1 = 0, x2 = 0;
         for (int j0 = 0; j0 < w; j0 += 32) {
-            sm.rec[lane] = make_pixrec(row, w, i, min(j0 + lane, w - 1), 0u);
+            if ((j0 & (kStageTile - 1)) == 0) rows.advance(i, j0, j0 + kStageTile < w ? i : -1, j0 + kStageTile, lane, 32, lane == 0);
+            {
+                const int jr = min(j0 + lane, w - 1) - (j0 & ~(kStageTile - 1));
+                sm.rec[lane] = make_pixrec_staged(rows.at(0, jr), rows.at(1, jr), 0u);
+            }
             __syncwarp();
             const int n_here = min(32, w - j0);
             u32 my_x = 0;

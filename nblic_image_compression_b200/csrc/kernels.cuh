@@ -41,6 +41,7 @@ struct Task {
 } /* namespace */
 #include "subwarp_nblic.cuh" /* needs Task */
 #include "pipe_qnblic.cuh"
+#include "pipe_nblic.cuh"
 namespace {
 
 constexpr int kChunkImagesPerSm = 192; /* host-buffer API: images per pipeline chunk and SM (multiple of 8, 16 and 24) */
@@ -147,32 +148,39 @@ __global__ void __launch_bounds__(32) coder_kernel(Task *tasks, const int *order
  * accumulators in `avp` (efforts 2 / 3: 2 * avp_half int64 per CTA).
  * MODE 0: lossless effort-1 encode (phase P = whole front end); 1: encode with a per-pixel front end
  * (near-lossless, and every effort-2/3 encode); 2: decode.  NAVP = 0 / 6 / 10 for effort 1 / 2 / 3. */
+/* Two independent one-warp streams share a CTA (kCoopWarps): shared memory is granted in 256-byte steps plus 1 KB per
+ * CTA, and a pair of streams wastes half of that -- 24 resident lossless effort-1 encoders per SM with the staged row
+ * tiles in place (22 as one-warp CTAs), 22 decoders (20).  The warps never synchronise with each other. */
+constexpr int kCoopWarps = 2;
 template <int NAVP, int MODE, bool RG>
-__global__ void __launch_bounds__(32) coop_nblic_kernel(Task *tasks, const int *order, int n_order, int *queue, int *counts, i64 *avp,
-                                                        size_t avp_half) {
-    extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(32 * kCoopWarps) coop_nblic_kernel(Task *tasks, const int *order, int n_order, int *queue, int *counts, i64 *avp,
+                                                                     size_t avp_half, u32 smem_per_warp) {
+    extern __shared__ __align__(16) uint8_t smem_all[];
     using L = CoopLayout<NAVP, MODE, RG>;
-    const int lane = threadIdx.x;
-    /* per-CTA global scratch: [512][20] int frequencies, then (efforts 2/3) the [512][20] byte rank tables */
-    uint8_t *my_scratch = reinterpret_cast<uint8_t *>(counts) + (size_t)blockIdx.x * (N_RANK_ENTRIES * 5);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t slot = (size_t)blockIdx.x * kCoopWarps + wid; /* this warp's index among the resident streams */
+    uint8_t *smem = smem_all + (size_t)wid * smem_per_warp;
+    /* per-stream global scratch: [512][20] int frequencies, then (efforts 2/3) the [512][20] byte rank tables */
+    uint8_t *my_scratch = reinterpret_cast<uint8_t *>(counts) + slot * (N_RANK_ENTRIES * 5);
     int *my_counts = reinterpret_cast<int *>(my_scratch);
     CoopSmem &sm = *reinterpret_cast<CoopSmem *>(smem);
     PixRec *recs = reinterpret_cast<PixRec *>(smem + L::kRecOff);
+    uint8_t *stage = smem + L::kStageOff;
     AvpSmem *asm_ = NAVP > 0 ? reinterpret_cast<AvpSmem *>(smem + L::kAvpOff) : nullptr;
     uint8_t *rank = L::kRankGlobal ? my_scratch + N_RANK_ENTRIES * 4 : smem + L::kRankOff;
     u32 *forest = reinterpret_cast<u32 *>(smem + L::kForestOff); /* sized by the host for the largest k_step of the launch */
-    i64 *my_b = NAVP > 0 ? avp + (size_t)blockIdx.x * 2 * avp_half : nullptr;
+    i64 *my_b = NAVP > 0 ? avp + slot * 2 * avp_half : nullptr;
     for (;;) {
         int pos = lane == 0 ? atomicAdd(queue, 1) : 0;
         pos = __shfl_sync(0xffffffffu, pos, 0);
         if (pos >= n_order) break;
         Task &t = tasks[order[pos]];
         u32 len;
-        if constexpr (MODE == 0) len = coop_e1_encode_lossless<RG>(t.src, t.h, t.w, t.slot, t.slot_cap, sm, rank, forest, my_counts, lane);
+        if constexpr (MODE == 0) len = coop_e1_encode_lossless<RG>(t.src, t.h, t.w, t.slot, t.slot_cap, sm, stage, rank, forest, my_counts, lane);
         else {
             const bool lossless_enc = MODE == 1 && t.near == 0; /* neighbours are the source pixels themselves */
             len = coop_feedback<NAVP, MODE == 2, RG>(t.src, lossless_enc ? t.src : t.rec, lossless_enc ? nullptr : t.rec, t.h, t.w, t.near, t.k_step,
-                                                 t.slot, t.slot_cap, sm, recs, asm_, rank, forest, my_b, my_b ? my_b + avp_half : nullptr, my_counts,
+                                                 t.slot, t.slot_cap, sm, recs, stage, asm_, rank, forest, my_b, my_b ? my_b + avp_half : nullptr, my_counts,
                                                  lane);
         }
         if (lane == 0) {
@@ -240,6 +248,17 @@ __global__ void __launch_bounds__(32) qpipe_finish_kernel(Task *tasks, const int
     if (lane == 0) {
         if (ok) { t.head_len = head * 2; t.tail_len = tail * 2; }
         else { t.status = NBLIC_B200_OVERFLOW; t.head_len = t.tail_len = 0; }
+    }
+}
+
+/* Last stage of the whole-GPU effort-1 encode (pipe_nblic.cuh): one warp codes the image's decisions. */
+__global__ void __launch_bounds__(32) e1p_coder_kernel(Task *tasks, int task_index, const uint16_t *coded, const unsigned long long *n_dec, const int *bad) {
+    Task &t = tasks[task_index];
+    const u32 len = *bad ? 0xffffffffu : e1p_code_stream(coded, *n_dec, t.h, t.w, t.k_step, t.slot, t.slot_cap, threadIdx.x);
+    if (threadIdx.x == 0) {
+        if (len == 0xffffffffu) { t.status = NBLIC_B200_OVERFLOW; t.head_len = 0; }
+        else t.head_len = len;
+        t.tail_len = 0;
     }
 }
 

@@ -45,6 +45,25 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+/* Page-locked host staging for the small per-call tables (task records, offsets, flags).  Copies between pageable host
+ * memory and the device make the driver wait for the stream INSIDE the copy call, which serialises the host threads of
+ * concurrent contexts (the lanes of split_over_lanes): measured, four lanes ran one after the other.  With pinned
+ * staging every copy is a plain asynchronous DMA and only cudaStreamSynchronize waits. */
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        const cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 thread_local std::string g_create_error; /* message of a failed nblic_b200_create on this thread */
 
 } /* namespace */
@@ -61,12 +80,19 @@ struct nblic_b200_ctx {
     float coder_ms = 0.f, coder_ms_total = 0.f; /* most recent batch call / accumulated by split_over_lanes */
     const char *last_map = "none";
     int last_slots = 0; /* resident streams the most recent cooperative launch could hold */
+    int co_streams = 0; /* lanes: streams of the whole batch, which share the GPU with this lane's piece (0 = this call is alone) */
     int sub_lps = getenv("NBLIC_B200_LPS") ? atoi(getenv("NBLIC_B200_LPS")) : 0; /* experiments: lanes per stream of the effort-1 decoder (32 = one stream per warp) */
     bool sub_forest_smem = getenv("NBLIC_B200_FOREST_SMEM") != nullptr;            /* experiments: counter forest in shared memory instead of L2 */
     int qpipe = getenv("NBLIC_B200_QPIPE") ? atoi(getenv("NBLIC_B200_QPIPE")) : -1; /* experiments: force (1) / forbid (0) the whole-GPU QNBLIC encode */                   /* experiments: whole bias table in shared memory */
+    int e1pipe = getenv("NBLIC_B200_E1PIPE") ? atoi(getenv("NBLIC_B200_E1PIPE")) : -1; /* experiments: force (1) / forbid (0) the whole-GPU effort-1 encode */
     DevBuf tasks, order, queue, slots, sym, cold, coop_counts, sub_scratch, pipe_meta, pipe_sorted, pipe_counts, avp, offsets, flags, pixels, streams, recon, peeks;
+    DevBuf e1p_rec, e1p_key, e1p_perm, e1p_counts, e1p_yz, e1p_doff, e1p_visrec, e1p_decrec, e1p_p1, e1p_totals; /* pipe_nblic.cuh stage buffers */
+    HostBuf h_tasks, h_order, h_small; /* pinned staging: task records both ways, launch order, offsets / flags / header peeks */
+    std::vector<DevBuf> e1p_coded;                                                                              /* one decision list per image of the batch */
+    cudaStream_t side = nullptr; /* the range-coder launches of the whole-GPU effort-1 encode */
+    cudaEvent_t ev_side = nullptr;
     int occ_warp[2] = {0, 0};
-    nblic_b200_ctx *lane[2] = {nullptr, nullptr}; /* host-buffer calls on large batches: two sub-contexts coding alternate pieces (see split_over_lanes) */
+    nblic_b200_ctx *lane[4] = {nullptr, nullptr, nullptr, nullptr}; /* host-buffer calls: sub-contexts coding the pieces of a batch side by side (see split_over_lanes) */
 };
 
 namespace {
@@ -153,23 +179,25 @@ int launch_coop_q(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_que
 
 template <int NAVP, int MODE, bool RG>
 int launch_coop_t(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w, int max_nodes, bool probe_only, int *slots_out) {
-    const size_t smem = CoopLayout<NAVP, MODE, RG>::kForestOff + sizeof(u32) * (size_t)max_nodes; /* fixed tables + the compacted counter forest */
+    /* per stream: fixed tables + the compacted counter forest; kCoopWarps streams per CTA */
+    const size_t per_warp = align_up(CoopLayout<NAVP, MODE, RG>::kForestOff + sizeof(u32) * (size_t)max_nodes, 16), smem = per_warp * kCoopWarps;
     auto kern = coop_nblic_kernel<NAVP, MODE, RG>;
     int per_sm = 0;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
-    const int slots = c->sm_count * std::max(per_sm, 1);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kCoopWarps, smem));
+    const int slots = c->sm_count * std::max(per_sm, 1) * kCoopWarps;
     if (slots_out) *slots_out = slots;
     if (probe_only) return 0;
-    int grid = balanced_grid(n_order, slots);
+    int streams = balanced_grid(n_order, slots);
     size_t avp_half = 0;
-    if (NAVP > 0) { /* B and F: one m-vector per image column each; bound the grid by a 32 GB budget */
+    if (NAVP > 0) { /* B and F: one m-vector per image column each; bound the resident streams by a 32 GB budget */
         avp_half = (size_t)max_w * (1 + NAVP + NAVP * NAVP);
-        grid = (int)std::min<size_t>((size_t)grid, std::max<size_t>(((size_t)32 << 30) / (2 * avp_half * sizeof(i64)), 1));
-        CK(c->avp.reserve((size_t)grid * 2 * avp_half * sizeof(i64)));
+        streams = (int)std::min<size_t>((size_t)streams, std::max<size_t>(((size_t)32 << 30) / (2 * avp_half * sizeof(i64)), 1));
     }
-    CK(c->coop_counts.reserve((size_t)grid * N_RANK_ENTRIES * 5)); /* frequencies (int) + rank tables (bytes) per CTA */
-    kern<<<grid, 32, smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (int *)c->coop_counts.p, (i64 *)c->avp.p, avp_half);
+    const int grid = (streams + kCoopWarps - 1) / kCoopWarps;
+    if (NAVP > 0) CK(c->avp.reserve((size_t)grid * kCoopWarps * 2 * avp_half * sizeof(i64)));
+    CK(c->coop_counts.reserve((size_t)grid * kCoopWarps * N_RANK_ENTRIES * 5)); /* frequencies (int) + rank tables (bytes) per stream */
+    kern<<<grid, 32 * kCoopWarps, smem, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (int *)c->coop_counts.p, (i64 *)c->avp.p, avp_half, (u32)per_warp);
     c->launches++;
     c->last_slots = slots;
     CK(cudaGetLastError());
@@ -222,6 +250,76 @@ int launch_qpipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, const
     return 0;
 }
 
+/* Stable partition of n items by keys[] (pipe_nblic.cuh): perm and key_start (NKEYS + 1 entries, inside c->e1p_counts). */
+template <int NKEYS>
+int e1p_sort(nblic_b200_ctx *c, const u32 *keys, long long n, u32 *perm, u32 **key_start_out) {
+    const int chunk_items = (int)std::max<long long>(4096, ((n + 1023) / 1024 + 31) / 32 * 32);
+    const int n_chunks = (int)std::max<long long>(1, (n + chunk_items - 1) / chunk_items);
+    u32 *counts = (u32 *)c->e1p_counts.p, *key_start = counts + (size_t)kE1NodeKeys * 1024; /* sized for the largest table by the caller */
+    psort_count_kernel<NKEYS><<<n_chunks, 256, 0, c->stream>>>(keys, n, chunk_items, n_chunks, counts);
+    psort_scan_kernel<<<1, 1024, 0, c->stream>>>(counts, NKEYS, n_chunks, key_start);
+    psort_scatter_kernel<NKEYS><<<n_chunks, 32, 0, c->stream>>>(keys, n, chunk_items, n_chunks, counts, perm);
+    c->launches += 3;
+    *key_start_out = key_start;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+/* Lossless effort-1 encode of few (large) images: every stage but the range coder uses the whole GPU, image after
+ * image on the context's stream; the range coders (one warp each) run on a side stream under the stages of the
+ * following images (pipe_nblic.cuh).  `idx` = task indices. */
+int launch_e1pipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, const std::vector<int> &idx) {
+    const int n = (int)idx.size();
+    if (!c->side) CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    if (!c->ev_side) CK(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+    if ((int)c->e1p_coded.size() < n) c->e1p_coded.resize((size_t)n);
+    CK(c->e1p_counts.reserve(((size_t)kE1NodeKeys * 1024 + kE1NodeKeys + 1) * sizeof(u32)));
+    CK(c->e1p_totals.reserve((size_t)n * 16));
+    CK(c->h_small.reserve(64));
+    CK(cudaMemsetAsync(c->e1p_totals.p, 0, (size_t)n * 16, c->stream));
+    const int wide = c->sm_count * 8;
+    for (int k = 0; k < n; k++) {
+        const Task &t = tasks[(size_t)idx[(size_t)k]];
+        const long long px = (long long)t.h * t.w;
+        const int blocks = (int)std::max<long long>(1, std::min<long long>((px + 255) / 256, wide));
+        unsigned long long *d_total = (unsigned long long *)((uint8_t *)c->e1p_totals.p + (size_t)k * 16);
+        int *d_bad = (int *)(d_total + 1);
+        CK(c->e1p_rec.reserve((size_t)px * 4)); CK(c->e1p_yz.reserve((size_t)px * 4)); CK(c->e1p_doff.reserve((size_t)px * 4));
+        CK(c->e1p_key.reserve((size_t)px * 4)); CK(c->e1p_perm.reserve((size_t)px * 4));
+        u32 *rec = (u32 *)c->e1p_rec.p, *yz = (u32 *)c->e1p_yz.p, *doff = (u32 *)c->e1p_doff.p, *key_start = nullptr;
+        e1p_front_kernel<<<blocks, 256, 0, c->stream>>>(t.src, t.h, t.w, rec, (u32 *)c->e1p_key.p);
+        if (e1p_sort<kE1BiasKeys>(c, (const u32 *)c->e1p_key.p, px, (u32 *)c->e1p_perm.p, &key_start)) return -1;
+        e1p_bias_kernel<<<kE1BiasKeys / 128, 128, 0, c->stream>>>((const u32 *)c->e1p_perm.p, key_start, rec, yz, (u32 *)c->e1p_key.p);
+        if (e1p_sort<kE1RankKeys>(c, (const u32 *)c->e1p_key.p, px, (u32 *)c->e1p_perm.p, &key_start)) return -1;
+        e1p_rank_kernel<<<kE1RankKeys / 64, 64, 0, c->stream>>>((const u32 *)c->e1p_perm.p, key_start, yz);
+        e1p_count_kernel<<<blocks, 256, 0, c->stream>>>(yz, px, t.k_step, doff, d_bad);
+        e1p_scan_kernel<<<1, 1024, 0, c->stream>>>(doff, px, d_total);
+        c->launches += 5;
+        CK(cudaMemcpyAsync(c->h_small.p, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream)); /* the decision count sizes the remaining buffers */
+        const unsigned long long n_dec = *(const unsigned long long *)c->h_small.p;
+        if (n_dec >= (1ull << 31)) { fail(c, "effort-1 pipeline: %llu decisions in one image", n_dec); return -1; }
+        const size_t nv = 2 * (size_t)n_dec;
+        CK(c->e1p_key.reserve(std::max<size_t>(nv, 1) * 4)); CK(c->e1p_perm.reserve(std::max<size_t>(nv, 1) * 4));
+        CK(c->e1p_visrec.reserve(std::max<size_t>(nv, 1))); CK(c->e1p_decrec.reserve(std::max<size_t>(n_dec, 1))); CK(c->e1p_p1.reserve(std::max<size_t>(nv, 1) * 2));
+        CK(c->e1p_coded[(size_t)k].reserve(std::max<size_t>(n_dec, 1) * 2));
+        e1p_emit_kernel<<<blocks, 256, 0, c->stream>>>(yz, px, t.k_step, doff, (u32 *)c->e1p_key.p, (uint8_t *)c->e1p_visrec.p, (uint8_t *)c->e1p_decrec.p);
+        if (e1p_sort<kE1NodeKeys>(c, (const u32 *)c->e1p_key.p, (long long)nv, (u32 *)c->e1p_perm.p, &key_start)) return -1;
+        e1p_node_kernel<<<kE1NodeKeys / 128, 128, 0, c->stream>>>((const u32 *)c->e1p_perm.p, key_start, (const uint8_t *)c->e1p_visrec.p, (uint16_t *)c->e1p_p1.p);
+        const int mix_blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n_dec + 255) / 256, (unsigned long long)wide));
+        e1p_mix_kernel<<<mix_blocks, 256, 0, c->stream>>>((const uint16_t *)c->e1p_p1.p, (const uint8_t *)c->e1p_decrec.p, n_dec, (uint16_t *)c->e1p_coded[(size_t)k].p);
+        c->launches += 3;
+        CK(cudaEventRecord(c->ev_side, c->stream));
+        CK(cudaStreamWaitEvent(c->side, c->ev_side, 0));
+        e1p_coder_kernel<<<1, 32, 0, c->side>>>((Task *)c->tasks.p, idx[(size_t)k], (const uint16_t *)c->e1p_coded[(size_t)k].p, d_total, d_bad);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev_side, c->side));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
+    return 0;
+}
+
 /* Effort-1 decode with 32 / LPS streams per warp; FORESTG: counter forest in L2 instead of shared memory. */
 template <int LPS, bool FORESTG>
 int launch_subwarp_t(nblic_b200_ctx *c, int n_packs, const int *d_packs, int *d_queue, int max_nodes) {
@@ -250,7 +348,7 @@ int launch_subwarp(nblic_b200_ctx *c, int lps, int n_packs, const int *d_packs, 
  * the one-stream-per-warp kernel keeps resident (issue-bound regime); below that, a stream alone in its warp is faster. */
 int choose_sub_lps(nblic_b200_ctx *c, int n_streams) {
     if (c->sub_lps == 8 || c->sub_lps == 32) return c->sub_lps;
-    return n_streams >= c->sm_count * 16 ? 8 : 32;
+    return std::max(n_streams, c->co_streams) >= c->sm_count * 16 ? 8 : 32;
 }
 
 /* Efforts 2/3 always keep the rank tables in L2.  Effort 1 keeps them in shared memory (lowest latency per
@@ -262,7 +360,7 @@ int launch_coop(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue
     int slots_smem = 0;
     if (launch_coop_t<NAVP, MODE, false>(c, n_order, d_order, d_queue, max_w, max_nodes, true, &slots_smem)) return -1;
     const char *force = getenv("NBLIC_B200_RANK");  /* "smem" / "l2": override for experiments */
-    const bool use_l2 = force ? force[0] == 'l' : n_order > slots_smem;
+    const bool use_l2 = force ? force[0] == 'l' : std::max(n_order, c->co_streams) > slots_smem;
     if (use_l2) return launch_coop_t<NAVP, MODE, true>(c, n_order, d_order, d_queue, max_w, max_nodes, false, nullptr);
     return launch_coop_t<NAVP, MODE, false>(c, n_order, d_order, d_queue, max_w, max_nodes, false, nullptr);
 }
@@ -322,8 +420,12 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
     CK(c->tasks.reserve(sizeof(Task) * (size_t)std::max(n, 1)));
     CK(c->order.reserve(sizeof(int) * std::max<size_t>(order.size(), 1)));
     CK(c->queue.reserve(N_GROUPS * sizeof(int)));
-    CK(cudaMemcpyAsync(c->tasks.p, tasks.data(), sizeof(Task) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    if (!order.empty()) CK(cudaMemcpyAsync(c->order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(c->h_tasks.reserve(sizeof(Task) * (size_t)std::max(n, 1)));
+    CK(c->h_order.reserve(sizeof(int) * std::max<size_t>(order.size(), 1)));
+    memcpy(c->h_tasks.p, tasks.data(), sizeof(Task) * (size_t)n);
+    memcpy(c->h_order.p, order.data(), sizeof(int) * order.size());
+    CK(cudaMemcpyAsync(c->tasks.p, c->h_tasks.p, sizeof(Task) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (!order.empty()) CK(cudaMemcpyAsync(c->order.p, c->h_order.p, sizeof(int) * order.size(), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->queue.p, 0, N_GROUPS * sizeof(int), c->stream));
 
     CK(cudaEventRecord(c->ev0, c->stream));
@@ -341,7 +443,11 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
                 else rc = coop_ok ? launch_coop_q<DEC>(c, cnt, d_ord, d_q) : launch_coder<KIND_Q, DEC>(c, cnt, d_ord, d_q, 1, 0);
                 break;
             case G_SEQ: rc = launch_coder<KIND_N, DEC>(c, cnt, d_ord, d_q, max_w[g], seq_effort); break;
-            case G_E1_LOSSLESS: rc = launch_coop<0, 0>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]); break;
+            case G_E1_LOSSLESS:
+                /* few images: the stages of every image spread over the whole GPU, only the range coders are one warp each */
+                if (c->e1pipe == 1 || (c->e1pipe != 0 && cnt <= 128 && c->co_streams == 0)) { rc = launch_e1pipe_encode(c, tasks, group[g]); pipelined = true; }
+                else rc = launch_coop<0, 0>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]);
+                break;
             case G_FB1:
                 if (sub_lps < 32) rc = launch_subwarp(c, sub_lps, n_packs, (const int *)c->order.p + packs_at, d_q, max_nodes[g]);
                 else rc = launch_coop<0, DEC ? 2 : 1>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]);
@@ -351,7 +457,7 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
         }
         if (rc) return -1;
         if (g >= G_E1_LOSSLESS || (g == G_Q && coop_ok)) c->last_map = "warp-coop";
-        if (g == G_Q && pipelined) c->last_map = "gpu-pipeline";
+        if ((g == G_Q || g == G_E1_LOSSLESS) && pipelined) c->last_map = "gpu-pipeline";
         if (g == G_FB1 && sub_lps < 32) c->last_map = "4-streams-per-warp";
     }
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -359,8 +465,9 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
 }
 
 int finish_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
-    CK(cudaMemcpyAsync(tasks.data(), c->tasks.p, sizeof(Task) * tasks.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_tasks.p, c->tasks.p, sizeof(Task) * tasks.size(), cudaMemcpyDeviceToHost, c->stream)); /* run_tasks sized h_tasks */
     CK(cudaStreamSynchronize(c->stream));
+    memcpy(tasks.data(), c->h_tasks.p, sizeof(Task) * tasks.size());
     CK(cudaEventElapsedTime(&c->coder_ms, c->ev0, c->ev1));
     return 0;
 }
@@ -417,6 +524,12 @@ void nblic_b200_destroy(nblic_b200_ctx *c) {
     if (c->copy) cudaStreamSynchronize(c->copy);
     DevBuf *bufs[] = {&c->tasks, &c->order, &c->queue, &c->slots, &c->sym, &c->cold, &c->coop_counts, &c->sub_scratch, &c->pipe_meta, &c->pipe_sorted, &c->pipe_counts, &c->avp, &c->offsets, &c->flags, &c->pixels, &c->streams, &c->recon, &c->peeks};
     for (DevBuf *b : bufs) b->release();
+    DevBuf *more[] = {&c->e1p_rec, &c->e1p_key, &c->e1p_perm, &c->e1p_counts, &c->e1p_yz, &c->e1p_doff, &c->e1p_visrec, &c->e1p_decrec, &c->e1p_p1, &c->e1p_totals};
+    for (DevBuf *b : more) b->release();
+    for (DevBuf &b : c->e1p_coded) b.release();
+    c->h_tasks.release(); c->h_order.release(); c->h_small.release();
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_copy) if (e) cudaEventDestroy(e);
@@ -434,6 +547,12 @@ int nblic_b200_set_mapping(nblic_b200_ctx *c, int mapping) {
     return 0;
 }
 
+int nblic_b200_set_pipeline(nblic_b200_ctx *c, int mode) {
+    if (!c || mode < NBLIC_B200_PIPE_AUTO || mode > NBLIC_B200_PIPE_ALWAYS) return -1;
+    c->qpipe = c->e1pipe = mode;
+    return 0;
+}
+
 uint64_t nblic_b200_launch_count(const nblic_b200_ctx *c) {
     if (!c) return 0;
     uint64_t total = c->launches;
@@ -444,6 +563,12 @@ float nblic_b200_last_coder_ms(const nblic_b200_ctx *c) { return c ? c->coder_ms
 const char *nblic_b200_last_mapping(const nblic_b200_ctx *c) { return c ? c->last_map : "none"; }
 int nblic_b200_last_slots(const nblic_b200_ctx *c) { return c ? c->last_slots : 0; }
 void *nblic_b200_stream_handle(const nblic_b200_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+void *nblic_b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) == cudaSuccess ? p : nullptr;
+}
+void nblic_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int nblic_b200_peek(const uint8_t *stream, size_t len, int *height, int *width, int *near, int *effort) {
     if (!stream) return -1;
@@ -513,10 +638,14 @@ int nblic_b200_encode_batch_device(nblic_b200_ctx *c, int n, const uint8_t *d_pi
                                                         stream_cap, chunk, (int *)c->flags.p);
     c->launches++;
     CK(cudaGetLastError());
-    int overflow = 0;
-    CK(cudaMemcpyAsync(stream_off, c->offsets.p, sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&overflow, c->flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c->h_small.reserve(sizeof(uint64_t) * ((size_t)n + 2)));
+    uint64_t *h_off = (uint64_t *)c->h_small.p;
+    int *h_flag = (int *)(h_off + n + 1);
+    CK(cudaMemcpyAsync(h_off, c->offsets.p, sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_flag, c->flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (finish_tasks(c, tasks)) return -1;
+    memcpy(stream_off, h_off, sizeof(uint64_t) * ((size_t)n + 1));
+    const int overflow = *h_flag;
     int failed = 0;
     for (int i = 0; i < n; i++) {
         int st = tasks[(size_t)i].status;
@@ -534,12 +663,15 @@ int decode_device_impl(nblic_b200_ctx *c, int n, const uint8_t *d_streams, const
     CK(c->offsets.reserve(sizeof(unsigned long long) * 2 * (size_t)n));
     CK(c->peeks.reserve(sizeof(Peek) * (size_t)n));
     unsigned long long *d_starts = (unsigned long long *)c->offsets.p, *d_lens = d_starts + n;
-    CK(cudaMemcpyAsync(d_starts, starts, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_lens, lens, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(c->h_small.reserve((2 * sizeof(uint64_t) + sizeof(Peek)) * (size_t)n));
+    uint64_t *h_starts = (uint64_t *)c->h_small.p;
+    Peek *peeks = (Peek *)(h_starts + 2 * (size_t)n);
+    memcpy(h_starts, starts, sizeof(uint64_t) * (size_t)n);
+    memcpy(h_starts + n, lens, sizeof(uint64_t) * (size_t)n);
+    CK(cudaMemcpyAsync(d_starts, h_starts, 2 * sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream)); /* d_lens follows d_starts */
     peek_headers_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(d_streams, d_starts, d_lens, n, (Peek *)c->peeks.p);
     c->launches++;
-    std::vector<Peek> peeks((size_t)n);
-    CK(cudaMemcpyAsync(peeks.data(), c->peeks.p, sizeof(Peek) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(peeks, c->peeks.p, sizeof(Peek) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
 
     std::vector<Task> tasks((size_t)n);
@@ -737,43 +869,59 @@ static int decode_batch_one_lane(nblic_b200_ctx *c, int n, const uint8_t *const 
 }
 
 /*
- * Host-buffer calls on large batches.  One lane = upload a piece, code it, download it, all on its own streams and
- * scratch.  Two lanes (two sub-contexts, one host thread each) take alternate pieces of the batch, so the PCIe traffic
- * of one piece rides under the kernels of the other, and the persistent grid of the next piece fills the SMs as the
- * previous one drains -- no kernel ever waits for another.  A piece is 24 images per SM: at least one full wave of every
- * coder kernel, small enough that the first upload and the last download (the only exposed copies) stay short.
+ * Host-buffer calls on batches of more than kLaneMinImagesPerSm images per SM.  One lane = upload a piece, code it,
+ * download it, all on its own streams and scratch (a sub-context driven by its own host thread).  The batch is cut into
+ * up to four pieces, one per lane, and the lanes run side by side: the pieces' kernels are co-resident, so the SMs see
+ * the same number of coder streams as one launch over the whole batch would give them (the coder kernels are
+ * latency-bound: their throughput is set by the resident streams), while the upload of piece k+1 rides under the
+ * kernels of pieces <= k and the download of piece k under those of pieces > k.  Exposed PCIe time: the first
+ * upload and the last download, i.e. about half of the traffic of ONE piece.
+ * (Round 2 first tried two lanes taking alternate pieces of 24 images per SM: each launch then held a quarter of the
+ * streams the 4-streams-per-warp decoder needs to fill the machine, and the end-to-end rate FELL to 0.53 of the
+ * device-resident one.)
  */
-constexpr int kLaneImagesPerSm = 24;
+constexpr int kLaneMinImagesPerSm = 8;
+constexpr int kLanePieceMax = 16384; /* bounds the per-lane scratch; larger batches give every lane several pieces */
 
 } /* extern "C" */
 
 template <class Piece>
 static int split_over_lanes(nblic_b200_ctx *c, int n, Piece piece) {
-    const int piece_n = c->sm_count * kLaneImagesPerSm;
-    for (nblic_b200_ctx *&l : c->lane) {
+    constexpr int kLanes = (int)(sizeof c->lane / sizeof c->lane[0]);
+    const int piece_n = std::min(kLanePieceMax, std::max(c->sm_count * 2, (n + kLanes - 1) / kLanes));
+    const int n_pieces = (n + piece_n - 1) / piece_n, lanes = std::min(kLanes, n_pieces);
+    for (int who = 0; who < lanes; who++) {
+        nblic_b200_ctx *&l = c->lane[who];
         if (!l) l = nblic_b200_create(c->device);
         if (!l) { fail(c, "lane context: %s", g_create_error.c_str()); return -1; }
         l->mapping = c->mapping;
         l->coder_ms_total = 0.f;
+        l->co_streams = n;
     }
-    const int n_pieces = (n + piece_n - 1) / piece_n;
-    int result[2] = {0, 0};
+    int result[kLanes] = {0, 0, 0, 0};
     auto work = [&](int who) {
-        for (int k = who; k < n_pieces; k += 2) {
+        for (int k = who; k < n_pieces; k += lanes) {
             const int lo = k * piece_n, cnt = std::min(n - lo, piece_n);
             const int rc = piece(c->lane[who], lo, cnt);
             if (rc < 0) { result[who] = -1; return; }
             result[who] += rc;
         }
     };
-    std::thread other(work, 1);
+    std::vector<std::thread> others;
+    for (int who = 1; who < lanes; who++) others.emplace_back(work, who);
     work(0);
-    other.join();
+    for (std::thread &t : others) t.join();
     c->coder_ms = 0.f;
-    for (nblic_b200_ctx *l : c->lane) { c->coder_ms += l->coder_ms_total; c->last_map = l->last_map; c->last_slots = l->last_slots; }
+    int total = 0;
+    for (int who = 0; who < lanes; who++) {
+        nblic_b200_ctx *l = c->lane[who];
+        c->coder_ms = std::max(c->coder_ms, l->coder_ms_total); /* the lanes overlap: the longest one, not the sum */
+        c->last_map = l->last_map; c->last_slots = l->last_slots;
+        if (result[who] < 0) { fail(c, "%s", l->error.c_str()); total = -1; }
+        else if (total >= 0) total += result[who];
+    }
     CK(cudaSetDevice(c->device));
-    if (result[0] < 0 || result[1] < 0) { fail(c, "%s", (result[0] < 0 ? c->lane[0] : c->lane[1])->error.c_str()); return -1; }
-    return result[0] + result[1];
+    return total;
 }
 
 extern "C" {
@@ -781,7 +929,7 @@ extern "C" {
 int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *images, const int *heights, const int *widths, int near,
                             int effort, uint8_t *const *outs, const size_t *out_caps, size_t *out_lens, uint8_t *const *recon, int *status) {
     if (!c) return -1;
-    if (n <= c->sm_count * kLaneImagesPerSm) return encode_batch_one_lane(c, n, images, heights, widths, near, effort, outs, out_caps, out_lens, recon, status);
+    if (n <= c->sm_count * kLaneMinImagesPerSm) return encode_batch_one_lane(c, n, images, heights, widths, near, effort, outs, out_caps, out_lens, recon, status);
     if (!images || !heights || !widths || !outs || !out_caps || !out_lens) { fail(c, "bad arguments"); return -1; }
     return split_over_lanes(c, n, [&](nblic_b200_ctx *l, int lo, int cnt) {
         const int rc = encode_batch_one_lane(l, cnt, images + lo, heights + lo, widths + lo, near, effort, outs + lo, out_caps + lo, out_lens + lo,
@@ -794,7 +942,7 @@ int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *imag
 int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *streams, const size_t *stream_lens, uint8_t *const *images,
                             const size_t *img_caps, int *heights, int *widths, int *nears, int *efforts, int *status) {
     if (!c) return -1;
-    if (n <= c->sm_count * kLaneImagesPerSm) return decode_batch_one_lane(c, n, streams, stream_lens, images, img_caps, heights, widths, nears, efforts, status);
+    if (n <= c->sm_count * kLaneMinImagesPerSm) return decode_batch_one_lane(c, n, streams, stream_lens, images, img_caps, heights, widths, nears, efforts, status);
     if (!streams || !stream_lens || !images || !img_caps) { fail(c, "bad arguments"); return -1; }
     return split_over_lanes(c, n, [&](nblic_b200_ctx *l, int lo, int cnt) {
         const int rc = decode_batch_one_lane(l, cnt, streams + lo, stream_lens + lo, images + lo, img_caps + lo, heights ? heights + lo : nullptr,

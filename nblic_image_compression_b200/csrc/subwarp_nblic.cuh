@@ -42,15 +42,11 @@ template <int LPS, bool FORESTG> struct SubLayout {
     static constexpr size_t kRankOff = (kFbaseOff + SPW * 32 + 15) & ~(size_t)15;  /* per stream: int count[20], u8 sym[32] = 112 B */
     static constexpr size_t kRecOff = kRankOff + SPW * 112;                        /* PixRec recs[LPS][SPW]                    */
     static constexpr size_t kCtxOff = kRecOff + sizeof(PixRec) * 32;               /* int16 ctx[SPW][256]: row cache           */
-    static constexpr size_t kForestOff = kCtxOff + (size_t)SPW * 256 * 2;          /* u32 forest[SPW][max_nodes] unless FORESTG */
+    static constexpr size_t kStageOff = kCtxOff + (size_t)SPW * 256 * 2;           /* per stream: staged tiles of rows i-1, i-2 (row_stage.cuh) */
+    static constexpr size_t kStagePerStream = 2 * 2 * kStageLine;
+    static constexpr size_t kForestOff = kStageOff + SPW * kStagePerStream;        /* u32 forest[SPW][max_nodes] unless FORESTG */
     static size_t bytes(int max_nodes) { return kForestOff + (FORESTG ? 0 : (size_t)SPW * max_nodes * 4); }
 };
-
-NB_DEV void cp_async16(void *smem_dst, const void *gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-NB_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 /* range decoder of one stream (R: NBLIC.c:541-572), registers uniform across the stream's lanes.  The look-ahead
  * `ahead` holds the next `navail` unread stream bytes left-aligned (first unread byte in bits 63..56); `wnext` is the
@@ -160,6 +156,8 @@ __device__ void subwarp_decode_pack(Task *tasks, const int *pack, uint8_t *smem,
         __syncwarp();
     }
     int cur_row = -1; /* class-pair row of the bias table held in ctx_s */
+    RowStage<2> rows; /* the two rows above, of this stream's own output */
+    rows.start(smem + L::kStageOff + sid * L::kStagePerStream, img, h, w);
 
     SubDecoder dec;
     dec.start(t.slot, live ? t.slot_cap : 0u);
@@ -170,7 +168,11 @@ __device__ void subwarp_decode_pack(Task *tasks, const int *pack, uint8_t *smem,
         uint8_t *row = img + (size_t)i * w;
         for (int j0 = 0; j0 < w; j0 += LPS) {
             /* ---------------- phase P: the rows above, sub-lane = pixel j0 + sl ---------------- */
-            if (i >= 1) recs[sl * SPW + sid] = make_pixrec(row, w, i, min(j0 + sl, w - 1), 0u);
+            if (i >= 2) { /* cp.async tiles of 64 pixels, the next one of this row in flight while this one is decoded */
+                if ((j0 & (kStageTile - 1)) == 0) rows.advance(i, j0, j0 + kStageTile < w ? i : -1, j0 + kStageTile, sl, LPS, sl == 0);
+                const int jr = min(j0 + sl, w - 1) - (j0 & ~(kStageTile - 1));
+                recs[sl * SPW + sid] = make_pixrec_staged(rows.at(0, jr), rows.at(1, jr), 0u);
+            } else if (i == 1) recs[sl * SPW + sid] = make_pixrec(row, w, i, min(j0 + sl, w - 1), 0u);
             __syncwarp();
 
             /* ---------------- phase S: one pixel of every stream at a time ---------------- */

@@ -37,13 +37,19 @@ def _oracle_enc(oracle, img, effort, near):
 
 def _check_batch(api, codec, oracle, images, effort, near, mapping):
     codec.set_mapping(mapping)
-    streams, recs, status = codec.encode_batch(images, near, effort, want_recon=near > 0)
-    assert all(s == api.OK for s in status)
     exp = [_oracle_enc(oracle, im, effort, near) for im in images]
-    for k, (s, e) in enumerate(zip(streams, exp)):
-        assert s == e[0], f"encode e{effort} n{near} image {k} {images[k].shape}"
-        if near:
-            assert np.array_equal(recs[k], e[1]), f"reconstruction e{effort} n{near} image {k}"
+    # lossless effort 0 / 1 have two encoders: one warp per image, and the whole-GPU single-image pipeline (N1)
+    modes = (api.PIPE_NEVER, api.PIPE_ALWAYS) if near == 0 and effort <= 1 and mapping != api.MAP_LANE else (api.PIPE_AUTO,)
+    for mode in modes:
+        codec.set_pipeline(mode)
+        streams, recs, status = codec.encode_batch(images, near, effort, want_recon=near > 0)
+        assert all(s == api.OK for s in status)
+        assert (codec.last_mapping == "gpu-pipeline") == (mode == api.PIPE_ALWAYS), (codec.last_mapping, mode)
+        for k, (s, e) in enumerate(zip(streams, exp)):
+            assert s == e[0], f"encode e{effort} n{near} image {k} {images[k].shape} pipeline mode {mode}"
+            if near:
+                assert np.array_equal(recs[k], e[1]), f"reconstruction e{effort} n{near} image {k}"
+    codec.set_pipeline(api.PIPE_AUTO)
     dec = codec.decode_batch([e[0] for e in exp])
     for k, (d, e) in enumerate(zip(dec, exp)):
         assert d is not None and np.array_equal(d[0], e[1]), f"decode e{effort} n{near} image {k}"
@@ -66,9 +72,12 @@ def test_kodak_e0_e1_golden(api, codec, kodak, manifest):
     names = sorted(kodak)
     images = [kodak[n] for n in names]
     codec.set_mapping(api.MAP_WARP)
-    for key, effort in (("e0n0", 0), ("e1n0", 1)):
+    for key, effort, mode in (("e0n0", 0, api.PIPE_NEVER), ("e1n0", 1, api.PIPE_NEVER), ("e0n0", 0, api.PIPE_ALWAYS), ("e1n0", 1, api.PIPE_ALWAYS)):
+        codec.set_pipeline(mode)  # one warp per image / every image spread over the whole GPU: same bytes
         streams, _, status = codec.encode_batch(images, 0, effort)
+        codec.set_pipeline(api.PIPE_AUTO)
         assert all(s == api.OK for s in status)
+        assert (codec.last_mapping == "gpu-pipeline") == (mode == api.PIPE_ALWAYS)
         total = 0
         for n, s in zip(names, streams):
             ent = manifest["kodak"][n]["streams"][key]
@@ -263,7 +272,11 @@ def test_batch_cli_matches_reference_cli(tmp_path, kodak):
         inputs.append(path)
     for switches in ("-cn0e0", "-cn0e1", "-cn3e1", "-cn1e3"):
         out = tmp_path / ("o" + switches[1:]); out.mkdir()
-        subprocess.run([cli, switches, str(out), *map(str, inputs)], check=True, stdout=subprocess.DEVNULL)
+        # "-b0" = one file per group: the reader / coder / writer pipeline runs over three groups instead of one
+        extra = ["-b0", "-v"] if switches == "-cn0e1" else []
+        res = subprocess.run([cli, switches, *extra, str(out), *map(str, inputs)], check=True, stdout=subprocess.PIPE, text=True)
+        if extra:
+            assert "3 images in 3 groups" in res.stdout and "pipeline of read" in res.stdout, res.stdout
         streams = []
         for path in inputs:
             ref_out = tmp_path / "ref.nblic"
@@ -272,7 +285,7 @@ def test_batch_cli_matches_reference_cli(tmp_path, kodak):
             assert mine.read_bytes() == ref_out.read_bytes(), (switches, path.name)
             streams.append(mine)
         dec = tmp_path / ("d" + switches[1:]); dec.mkdir()
-        subprocess.run([cli, "-d", str(dec), *map(str, streams)], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([cli, "-d", *extra[:1], str(dec), *map(str, streams)], check=True, stdout=subprocess.DEVNULL)
         for path in streams:
             ref_pgm = tmp_path / "ref.pgm"
             subprocess.run([theirs, "-d", str(path), str(ref_pgm)], check=True, stdout=subprocess.DEVNULL)
@@ -332,7 +345,11 @@ def test_random_fuzz_vs_checker(api, codec, oracle):
             imgs.append(im)
         effort = trial % 4
         near = 0 if effort == 0 else int(rng.integers(0, 10))
+        if trial in (1, 5):
+            near = 0  # lossless effort 1 through the single-image pipeline (trial 1) and the per-warp encoder (trial 5)
+        codec.set_pipeline(api.PIPE_ALWAYS if trial % 8 < 4 else api.PIPE_NEVER)
         streams, recs, status = codec.encode_batch(imgs, near, effort, want_recon=near > 0)
+        codec.set_pipeline(api.PIPE_AUTO)
         assert all(s == api.OK for s in status)
         exp = [(chk.q_encode(im), im) if effort == 0 else chk.n_encode(im, near, effort)[:2] for im in imgs]
         for k, (s, e) in enumerate(zip(streams, exp)):
