@@ -21,9 +21,10 @@
  *   e1p_mix_kernel       lane per decision: mixed probability | bit << 12                         R: NBLIC.c:620-637
  *   e1p_coder_kernel     one warp per image: the range coder, the only serial stage               R: NBLIC.c:527-586
  *
- * The stable partition is three small kernels (psort_*): per-chunk key histogram, one scan over (key, chunk), and a
- * scatter that walks each chunk in order, 32 items a step, ranking equal keys of a step with __match_any.  It yields a
- * PERMUTATION (sorted position -> item index); the chain kernels gather their records through it.
+ * The stable partition is four small kernels (psort_*): per-chunk key histogram, a scan over the chunks of every key
+ * and one over the keys, and a scatter that walks each chunk in order, 32 items a step, ranking equal keys of a step
+ * with __match_any.  It yields the PERMUTATION (sorted position -> item index) and the items' records in sorted order, so
+ * a chain kernel streams its input sequentially (16-byte loads, one batch ahead of the chain) and only scatters results.
  *
  * What is left of the latency is the range coder (~40 cycles per decision, ~4.6 decisions per pixel): an image encodes
  * at about the speed of one CPU core instead of 6 times slower, and the images of a small batch overlap completely.
@@ -49,40 +50,58 @@ __global__ void __launch_bounds__(256) psort_count_kernel(const u32 *keys, long 
     for (int k = threadIdx.x; k < NKEYS; k += blockDim.x) counts[(size_t)k * n_chunks + blockIdx.x] = hist[k];
 }
 
-/* In place: counts -> exclusive prefix in (key-major, chunk-minor) order; key_start[key] = first slot of the key,
- * key_start[n_keys] = number of items that took part.  One CTA of 1024 threads, thread t owns a contiguous piece. */
-__global__ void __launch_bounds__(1024) psort_scan_kernel(u32 *counts, int n_keys, int n_chunks, u32 *key_start) {
-    __shared__ unsigned long long part[1024];
-    const size_t total = (size_t)n_keys * n_chunks;
-    const size_t per = (total + 1023) / 1024;
-    const size_t lo = min(total, per * threadIdx.x), hi = min(total, lo + per);
-    unsigned long long s = 0;
-    for (size_t k = lo; k < hi; k++) s += counts[k];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned long long mine = 0;
-        for (int k = 0; k < 32; k++) mine += part[threadIdx.x * 32 + k];
-        unsigned long long incl = mine;
+/* Scan, step 1: one warp per key turns the key's per-chunk counts (contiguous) into exclusive prefixes in place and
+ * leaves the key's total in key_total[key]. */
+__global__ void __launch_bounds__(256) psort_scan_keys_kernel(u32 *counts, int n_keys, int n_chunks, u32 *key_total) {
+    const int lane = threadIdx.x & 31, key = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (key >= n_keys) return;
+    u32 *row = counts + (size_t)key * n_chunks;
+    u32 carry = 0;
+    for (int base = 0; base < n_chunks; base += 32) {
+        const int c = base + lane;
+        const u32 v = c < n_chunks ? row[c] : 0u;
+        u32 incl = v;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d); if ((int)threadIdx.x >= d) incl += o; }
-        unsigned long long run = incl - mine;
-        for (int k = 0; k < 32; k++) { const unsigned long long v = part[threadIdx.x * 32 + k]; part[threadIdx.x * 32 + k] = run; run += v; }
+        for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+        if (c < n_chunks) row[c] = carry + incl - v;
+        carry += __shfl_sync(FULL, incl, 31);
+    }
+    if (lane == 0) key_total[key] = carry;
+}
+/* Scan, step 2: key_start[key] = items with a smaller key (exclusive scan of key_total, n_keys <= 4096), key_start[n_keys]
+ * = items that took part.  One CTA of 1024 threads, four keys each. */
+__global__ void __launch_bounds__(1024) psort_scan_totals_kernel(const u32 *key_total, int n_keys, u32 *key_start) {
+    __shared__ u32 warp_sum[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 v[4], mine = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int key = 4 * threadIdx.x + k; v[k] = key < n_keys ? key_total[key] : 0u; mine += v[k]; }
+    u32 incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        u32 s = warp_sum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(FULL, s, d); if (lane >= d) s += o; }
+        warp_sum[lane] = s;
     }
     __syncthreads();
-    unsigned long long run = part[threadIdx.x];
-    for (size_t k = lo; k < hi; k++) { const u32 v = counts[k]; counts[k] = (u32)run; run += v; }
-    if (threadIdx.x == 1023) key_start[n_keys] = (u32)run;
-    __syncthreads();
-    for (int key = threadIdx.x; key < n_keys; key += 1024) key_start[key] = counts[(size_t)key * n_chunks];
+    u32 run = (wid ? warp_sum[wid - 1] : 0u) + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int key = 4 * threadIdx.x + k; if (key < n_keys) key_start[key] = run; run += v[k]; }
+    if (threadIdx.x == 1023) key_start[n_keys] = warp_sum[31];
 }
 
-/* perm[slot] = item index; one warp per chunk, in item order inside the chunk => stable */
-template <int NKEYS>
-__global__ void __launch_bounds__(32) psort_scatter_kernel(const u32 *keys, long long n, int chunk_items, int n_chunks, const u32 *offsets, u32 *perm) {
+/* perm[slot] = item index and sorted[slot] = payload[item]; one warp per chunk, in item order inside the chunk => stable.
+ * offsets = the per-key exclusive prefixes of step 1, key_start the key bases of step 2. */
+template <int NKEYS, class T>
+__global__ void __launch_bounds__(32) psort_scatter_kernel(const u32 *keys, const T *payload, long long n, int chunk_items, int n_chunks, const u32 *offsets,
+                                                           const u32 *key_start, u32 *perm, T *sorted) {
     __shared__ u32 next[NKEYS];
     const int lane = threadIdx.x;
-    for (int k = lane; k < NKEYS; k += 32) next[k] = offsets[(size_t)k * n_chunks + blockIdx.x];
+    for (int k = lane; k < NKEYS; k += 32) next[k] = key_start[k] + offsets[(size_t)k * n_chunks + blockIdx.x];
     __syncwarp();
     const long long lo = (long long)blockIdx.x * chunk_items, hi = min(n, lo + chunk_items);
     for (long long base = lo; base < hi; base += 32) {
@@ -91,7 +110,7 @@ __global__ void __launch_bounds__(32) psort_scatter_kernel(const u32 *keys, long
         const bool active = key != kSortSkip;
         const unsigned peers = __match_any_sync(FULL, active ? key : 0x80000000u + (u32)lane);
         const int before = __popc(peers & ((1u << lane) - 1u));
-        if (active) perm[next[key] + (u32)before] = (u32)p;
+        if (active) { const u32 slot = next[key] + (u32)before; perm[slot] = (u32)p; sorted[slot] = payload[p]; }
         __syncwarp();
         if (active && before == __popc(peers) - 1) next[key] += (u32)__popc(peers); /* the last member of a group advances its cursor */
         __syncwarp();
@@ -153,55 +172,67 @@ __global__ void __launch_bounds__(256) e1p_front_kernel(const uint8_t *img, int 
     }
 }
 
+/* ---- chain input: a lane walks [lo, hi) of two sorted arrays, eight items a batch, the next batch in flight ---- */
+template <class T> struct ChainBatch { u32 idx[8]; T rec[8]; };
+template <class T>
+NB_DEV void chain_load(ChainBatch<T> &b, const u32 *perm, const T *sorted, u32 base, u32 hi) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) { const bool in = base + u < hi; b.idx[u] = in ? __ldg(perm + base + u) : 0u; b.rec[u] = in ? __ldg(sorted + base + u) : T(0); }
+}
+
 /* ---- stage 2: bias chains ------------------------------------------------------------------------------ */
 /* One lane per bias-table entry; out: yz[p] = y | px << 8 | sign << 16 | soft << 17; rank key[p] = (px << 1 | sign) or skip. */
-__global__ void __launch_bounds__(128) e1p_bias_kernel(const u32 *perm, const u32 *key_start, const u32 *rec, u32 *yz, u32 *rank_key) {
+__global__ void __launch_bounds__(128) e1p_bias_kernel(const u32 *perm, const u32 *sorted_rec, const u32 *key_start, u32 *yz, u32 *rank_key) {
     const int adr = blockIdx.x * blockDim.x + threadIdx.x;
     if (adr >= kE1BiasKeys) return;
     const u32 lo = key_start[adr], hi = key_start[adr + 1];
     int c = 0;
-    for (u32 base = lo; base < hi; base += 8) { /* eight independent gathers in flight, then the chain */
-        u32 idx[8], r[8];
+    ChainBatch<u32> cur, nxt;
+    chain_load(cur, perm, sorted_rec, lo, hi);
+    for (u32 base = lo; base < hi; base += 8) {
+        chain_load(nxt, perm, sorted_rec, base + 8, hi);
+        int before[8]; /* the table entry each pixel sees */
 #pragma unroll
-        for (int u = 0; u < 8; u++) idx[u] = base + u < hi ? __ldg(perm + base + u) : 0u;
+        for (int u = 0; u < 8; u++) { /* the chain proper: the update uses x - px0, not the corrected prediction */
+            before[u] = c;
+            if (base + u < hi) c = n_bias_learn(c, clampi((int)((cur.rec[u] >> 8) & 255u) - (int)(cur.rec[u] & 255u), -127, 127));
+        }
 #pragma unroll
-        for (int u = 0; u < 8; u++) r[u] = base + u < hi ? __ldg(rec + idx[u]) : 0u;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < 8; u++) { /* independent of each other */
             if (base + u < hi) {
-                const int px0 = (int)(r[u] & 255u), x = (int)((r[u] >> 8) & 255u);
+                const u32 r = cur.rec[u];
+                const int px0 = (int)(r & 255u), x = (int)((r >> 8) & 255u);
                 int px, sign;
-                n_bias_apply(c, px0, px, sign);
+                n_bias_apply(before[u], px0, px, sign);
                 const int room = min(px, 255 - px), mag = abs(x - px);
                 const int y = mag == 0 ? 0 : (mag <= room ? 2 * mag - ((x >= px) ^ sign) : mag + room);
-                c = n_bias_learn(c, clampi(x - px0, -127, 127));
-                yz[idx[u]] = (u32)y | ((u32)px << 8) | ((u32)sign << 16) | ((r[u] >> 16) << 17);
-                rank_key[idx[u]] = y < N_RANKS ? (u32)((px << 1) | sign) : kSortSkip;
+                yz[cur.idx[u]] = (u32)y | ((u32)px << 8) | ((u32)sign << 16) | ((r >> 16) << 17);
+                rank_key[cur.idx[u]] = y < N_RANKS ? (u32)((px << 1) | sign) : kSortSkip;
             }
         }
+        cur = nxt;
     }
 }
 
 /* ---- stage 3: rank-mapper chains ------------------------------------------------------------------------ */
 /* One lane per key, tables interleaved in shared memory ([entry][lane]: conflict free).  Rewrites the y field of yz[p]
- * with the rank z for the pixels that go through the mapper. */
-__global__ void __launch_bounds__(64) e1p_rank_kernel(const u32 *perm, const u32 *key_start, u32 *yz) {
+ * with the rank z for the pixels that go through the mapper (sorted_yz = their yz words in chain order). */
+__global__ void __launch_bounds__(64) e1p_rank_kernel(const u32 *perm, const u32 *sorted_yz, const u32 *key_start, u32 *yz) {
     __shared__ int cnt[N_RANKS][64];
     __shared__ uint8_t rank_of[N_RANKS][64], sym_at[N_RANKS][64];
     const int t = threadIdx.x, key = blockIdx.x * 64 + t;
     for (int r = 0; r < N_RANKS; r++) { cnt[r][t] = 2 * (N_RANKS - 1 - r); rank_of[r][t] = (uint8_t)r; sym_at[r][t] = (uint8_t)r; }
     if (key >= kE1RankKeys) return;
     const u32 lo = key_start[key], hi = key_start[key + 1];
+    ChainBatch<u32> cur, nxt;
+    chain_load(cur, perm, sorted_yz, lo, hi);
     for (u32 base = lo; base < hi; base += 8) {
-        u32 idx[8], v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) idx[u] = base + u < hi ? __ldg(perm + base + u) : 0u;
-#pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = base + u < hi ? yz[idx[u]] : 0u;
+        chain_load(nxt, perm, sorted_yz, base + 8, hi);
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             if (base + u < hi) {
-                const int y = (int)(v[u] & 255u);
+                const u32 v = cur.rec[u];
+                const int y = (int)(v & 255u);
                 const int z = rank_of[y][t];
                 const int cz = cnt[z][t] + 1;
                 bool promoted = false;
@@ -216,9 +247,10 @@ __global__ void __launch_bounds__(64) e1p_rank_kernel(const u32 *perm, const u32
                     }
                 }
                 if (!promoted) cnt[z][t] = cz;
-                yz[idx[u]] = (v[u] & ~255u) | (u32)z;
+                yz[cur.idx[u]] = (v & ~255u) | (u32)z;
             }
         }
+        cur = nxt;
     }
 }
 
@@ -249,25 +281,47 @@ NB_DEV int e1p_walk(int k_step, int top, int u, int v, int z, Emit emit) {
     return n;
 }
 
-/* dcount[p] = decisions of pixel p; *bad is raised for an escape past the last order */
-__global__ void __launch_bounds__(256) e1p_count_kernel(const u32 *yz, long long n, int k_step, u32 *dcount, int *bad) {
-    const int top = (N_CLASSES - 1) / k_step;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
-        const u32 v = yz[p];
-        const int soft = (int)(v >> 17);
-        const int cnt = e1p_walk(k_step, top, soft & 15, (soft >> 4) & 15, (int)(v & 255u), [](int, int, int, int) {});
-        if (cnt < 0) { atomicExch(bad, 1); dcount[p] = 0; } else dcount[p] = (u32)cnt;
+/* doff[p] = decisions of the pixels before p inside p's block of kE1ScanBlock pixels; block_sums[b] = decisions of block
+ * b; *bad is raised for an escape past the last order.  Thread t of a CTA owns 16 consecutive pixels. */
+constexpr int kE1ScanBlock = 4096;
+__global__ void __launch_bounds__(256) e1p_count_kernel(const u32 *yz, long long n, int k_step, u32 *doff, u32 *block_sums, int *bad) {
+    __shared__ u32 warp_sum[8];
+    const int top = (N_CLASSES - 1) / k_step, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long first = (long long)blockIdx.x * kE1ScanBlock + 16 * threadIdx.x;
+    u32 cnt[16], mine = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const long long p = first + i;
+        cnt[i] = 0;
+        if (p < n) {
+            const u32 v = yz[p];
+            const int soft = (int)(v >> 17);
+            const int d = e1p_walk(k_step, top, soft & 15, (soft >> 4) & 15, (int)(v & 255u), [](int, int, int, int) {});
+            if (d < 0) atomicExch(bad, 1); else cnt[i] = (u32)d;
+        }
+        mine += cnt[i];
     }
+    u32 incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    u32 run = incl - mine;
+    for (int k = 0; k < wid; k++) run += warp_sum[k];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { const long long p = first + i; if (p < n) doff[p] = run; run += cnt[i]; }
+    if (threadIdx.x == 255) block_sums[blockIdx.x] = run;
 }
 
 /* visit 2g + role of decision g: vis_key = node (side class: skip when both classes share the node),
  * vis_rec = bit | weight << 1 | same << 7; dec_rec[g] = wv | bit << 5 */
-__global__ void __launch_bounds__(256) e1p_emit_kernel(const u32 *yz, long long n, int k_step, const u32 *doff, u32 *vis_key, uint8_t *vis_rec, uint8_t *dec_rec) {
+__global__ void __launch_bounds__(256) e1p_emit_kernel(const u32 *yz, long long n, int k_step, const u32 *doff, const u32 *block_off, u32 *vis_key,
+                                                       uint8_t *vis_rec, uint8_t *dec_rec) {
     const int top = (N_CLASSES - 1) / k_step;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
         const u32 v = yz[p];
         const int soft = (int)(v >> 17), wv = (soft >> 8) & 31;
-        const size_t g0 = doff[p];
+        const size_t g0 = (size_t)doff[p] + block_off[p / kE1ScanBlock];
         e1p_walk(k_step, top, soft & 15, (soft >> 4) & 15, (int)(v & 255u), [&](int d, int nu, int nv, int bit) {
             const size_t g = g0 + (size_t)d;
             const bool same = nu == nv;
@@ -282,31 +336,35 @@ __global__ void __launch_bounds__(256) e1p_emit_kernel(const u32 *yz, long long 
 
 /* ---- stage 5: counter-node chains ------------------------------------------------------------------------- */
 /* One lane per node; p1[visit] = floor(4096 n1 / (n0 + n1)) before the visit's update. */
-__global__ void __launch_bounds__(128) e1p_node_kernel(const u32 *perm, const u32 *key_start, const uint8_t *vis_rec, uint16_t *p1) {
+__global__ void __launch_bounds__(128) e1p_node_kernel(const u32 *perm, const uint8_t *sorted_rec, const u32 *key_start, uint16_t *p1) {
     const int node = blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= kE1NodeKeys) return;
     const u32 lo = key_start[node], hi = key_start[node + 1];
     u32 c = (u32)N_MIX | ((u32)N_MIX << 16);
+    ChainBatch<uint8_t> cur, nxt;
+    chain_load(cur, perm, sorted_rec, lo, hi);
     for (u32 base = lo; base < hi; base += 8) {
-        u32 idx[8], r[8];
+        chain_load(nxt, perm, sorted_rec, base + 8, hi);
+        u32 before[8]; /* the counter pair each visit sees */
 #pragma unroll
-        for (int u = 0; u < 8; u++) idx[u] = base + u < hi ? __ldg(perm + base + u) : 0u;
-#pragma unroll
-        for (int u = 0; u < 8; u++) r[u] = base + u < hi ? (u32)__ldg(vis_rec + idx[u]) : 0u;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < 8; u++) { /* the chain proper: six dependent operations a visit */
+            before[u] = c;
             if (base + u < hi) {
-                const u32 s = pair_sum(c);
-                const int bit = (int)(r[u] & 1u), weight = (int)((r[u] >> 1) & 63u);
-                const uint16_t p = (uint16_t)node_p1_fast(c, s);
-                p1[idx[u]] = p;
-                c = learn_packed(c, s, bit, weight);
-                if (r[u] & 0x80u) { /* both classes are this node: it learns the side weight too (R: NBLIC.c:633-636) */
-                    p1[idx[u] + 1] = p;
-                    c = learn_packed(c, pair_sum(c), bit, N_MIX - weight);
-                }
+                const u32 r = cur.rec[u];
+                const int bit = (int)(r & 1u), weight = (int)((r >> 1) & 63u);
+                c = learn_packed(c, pair_sum(c), bit, weight);
+                if (r & 0x80u) c = learn_packed(c, pair_sum(c), bit, N_MIX - weight); /* both classes are this node: it learns the side weight too (R: NBLIC.c:633-636) */
             }
         }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { /* the eight probabilities are independent of each other: they pipeline */
+            if (base + u < hi) {
+                const uint16_t p = (uint16_t)node_p1_fast(before[u], pair_sum(before[u]));
+                p1[cur.idx[u]] = p;
+                if (cur.rec[u] & 0x80u) p1[cur.idx[u] + 1] = p;
+            }
+        }
+        cur = nxt;
     }
 }
 
@@ -330,9 +388,20 @@ __device__ u32 e1p_code_stream(const uint16_t *coded, unsigned long long n_dec, 
         const unsigned long long nb = base + 32 + lane;
         const u32 nxt = nb < n_dec ? coded[nb] : 0u; /* one block ahead */
         const int cnt = (int)min(32ull, n_dec - base);
-        for (int e = 0; e < cnt; e++) {
-            const u32 cd = __shfl_sync(FULL, cur, e);
-            rc.bit((int)(cd >> 12), cd & 0xfffu);
+        if (cnt == 32) { /* eight decisions' shuffles are issued ahead of the eight coder steps: a shuffle in front of every step
+                          * (~25 cycles) was two thirds of the chain of this lone warp */
+            for (int g = 0; g < 32; g += 8) {
+                u32 cd[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) cd[k] = __shfl_sync(FULL, cur, g + k);
+#pragma unroll
+                for (int k = 0; k < 8; k++) rc.bit((int)(cd[k] >> 12), cd[k] & 0xfffu);
+            }
+        } else {
+            for (int e = 0; e < cnt; e++) {
+                const u32 cd = __shfl_sync(FULL, cur, e);
+                rc.bit((int)(cd >> 12), cd & 0xfffu);
+            }
         }
         cur = nxt;
     }

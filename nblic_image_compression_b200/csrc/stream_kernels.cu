@@ -17,6 +17,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -29,20 +31,24 @@ namespace {
 
 /* ---- host-side helpers ----------------------------------------------------------------------- */
 
+/* Device scratch that only grows.  Stream-ordered allocation (cudaMallocAsync / cudaFreeAsync on the owning context's
+ * stream): cudaFree would wait for EVERY stream of the device, i.e. for the kernels of other contexts -- a context that
+ * grows a buffer, or is destroyed, next to another context's minutes-long single-image launch must not stall on it. */
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    cudaStream_t st = nullptr; /* set by nblic_b200_create */
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        release();
         size_t want = bytes + bytes / 8 + 4096;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
-        if (e == cudaSuccess) cap = want;
+        cudaError_t e = cudaMallocAsync(&p, want, st);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); want = bytes; e = cudaMallocAsync(&p, want, st); }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) cap = want; else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; cap = 0; }
 };
 
 /* Page-locked host staging for the small per-call tables (task records, offsets, flags).  Copies between pageable host
@@ -54,14 +60,31 @@ struct HostBuf {
     size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
+        release();
         const size_t want = bytes + bytes / 4 + 4096;
+        if (pool_take(want, &p, &cap)) return cudaSuccess;
         const cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
-        if (e == cudaSuccess) cap = want;
+        if (e == cudaSuccess) cap = want; else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    void release() { if (p) pool_give(p, cap); p = nullptr; cap = 0; }
+
+    /* Released staging goes to a process-wide free list instead of cudaFreeHost (which, like cudaFree, waits for the
+     * whole device); the list is bounded by the peak staging ever in use -- a few hundred bytes per image. */
+    struct Spare { void *p; size_t cap; };
+    static std::mutex &pool_lock() { static std::mutex m; return m; }
+    static std::vector<Spare> &pool() { static std::vector<Spare> v; return v; }
+    static bool pool_take(size_t want, void **out, size_t *cap_out) {
+        std::lock_guard<std::mutex> g(pool_lock());
+        std::vector<Spare> &v = pool();
+        size_t best = v.size();
+        for (size_t k = 0; k < v.size(); k++) if (v[k].cap >= want && (best == v.size() || v[k].cap < v[best].cap)) best = k;
+        if (best == v.size()) return false;
+        *out = v[best].p; *cap_out = v[best].cap;
+        v.erase(v.begin() + (long)best);
+        return true;
+    }
+    static void pool_give(void *q, size_t c) { std::lock_guard<std::mutex> g(pool_lock()); pool().push_back({q, c}); }
 };
 
 thread_local std::string g_create_error; /* message of a failed nblic_b200_create on this thread */
@@ -86,16 +109,27 @@ struct nblic_b200_ctx {
     int qpipe = getenv("NBLIC_B200_QPIPE") ? atoi(getenv("NBLIC_B200_QPIPE")) : -1; /* experiments: force (1) / forbid (0) the whole-GPU QNBLIC encode */                   /* experiments: whole bias table in shared memory */
     int e1pipe = getenv("NBLIC_B200_E1PIPE") ? atoi(getenv("NBLIC_B200_E1PIPE")) : -1; /* experiments: force (1) / forbid (0) the whole-GPU effort-1 encode */
     DevBuf tasks, order, queue, slots, sym, cold, coop_counts, sub_scratch, pipe_meta, pipe_sorted, pipe_counts, avp, offsets, flags, pixels, streams, recon, peeks;
-    DevBuf e1p_rec, e1p_key, e1p_perm, e1p_counts, e1p_yz, e1p_doff, e1p_visrec, e1p_decrec, e1p_p1, e1p_totals; /* pipe_nblic.cuh stage buffers */
     HostBuf h_tasks, h_order, h_small; /* pinned staging: task records both ways, launch order, offsets / flags / header peeks */
-    std::vector<DevBuf> e1p_coded;                                                                              /* one decision list per image of the batch */
-    cudaStream_t side = nullptr; /* the range-coder launches of the whole-GPU effort-1 encode */
-    cudaEvent_t ev_side = nullptr;
+    /* whole-GPU effort-1 encode (pipe_nblic.cuh): images in flight side by side, each on its own stream and scratch set */
+    struct E1Set {
+        DevBuf rec, key, perm, sorted, counts, yz, doff, sums, visrec, decrec, p1, coded, totals;
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf *all[13] = {&rec, &key, &perm, &sorted, &counts, &yz, &doff, &sums, &visrec, &decrec, &p1, &coded, &totals};
+    };
+    enum { kE1Sets = 32 };
+    std::vector<E1Set> e1p;
+    cudaEvent_t ev_e1 = nullptr; /* marks the task-table upload for the sets' streams */
     int occ_warp[2] = {0, 0};
     nblic_b200_ctx *lane[4] = {nullptr, nullptr, nullptr, nullptr}; /* host-buffer calls: sub-contexts coding the pieces of a batch side by side (see split_over_lanes) */
 };
 
 namespace {
+
+std::vector<DevBuf *> all_buffers(nblic_b200_ctx *c) {
+    return {&c->tasks, &c->order, &c->queue, &c->slots, &c->sym, &c->cold, &c->coop_counts, &c->sub_scratch, &c->pipe_meta, &c->pipe_sorted, &c->pipe_counts,
+            &c->avp, &c->offsets, &c->flags, &c->pixels, &c->streams, &c->recon, &c->peeks};
+}
 
 bool fail(nblic_b200_ctx *c, const char *fmt, ...) {
     char buf[512];
@@ -250,73 +284,165 @@ int launch_qpipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, const
     return 0;
 }
 
-/* Stable partition of n items by keys[] (pipe_nblic.cuh): perm and key_start (NKEYS + 1 entries, inside c->e1p_counts). */
-template <int NKEYS>
-int e1p_sort(nblic_b200_ctx *c, const u32 *keys, long long n, u32 *perm, u32 **key_start_out) {
-    const int chunk_items = (int)std::max<long long>(4096, ((n + 1023) / 1024 + 31) / 32 * 32);
-    const int n_chunks = (int)std::max<long long>(1, (n + chunk_items - 1) / chunk_items);
-    u32 *counts = (u32 *)c->e1p_counts.p, *key_start = counts + (size_t)kE1NodeKeys * 1024; /* sized for the largest table by the caller */
-    psort_count_kernel<NKEYS><<<n_chunks, 256, 0, c->stream>>>(keys, n, chunk_items, n_chunks, counts);
-    psort_scan_kernel<<<1, 1024, 0, c->stream>>>(counts, NKEYS, n_chunks, key_start);
-    psort_scatter_kernel<NKEYS><<<n_chunks, 32, 0, c->stream>>>(keys, n, chunk_items, n_chunks, counts, perm);
-    c->launches += 3;
-    *key_start_out = key_start;
-    CK(cudaGetLastError());
-    return 0;
+/* The launches of one image's pipeline, in stream order.  Several images are in flight on their own streams; their
+ * launch lists are issued BREADTH FIRST (step s of every image, then step s + 1): the streams share the device's few
+ * hardware work queues, and depth-first issue would park image k + 8's short stage kernels in the queue behind image k's
+ * chain of dependent launches (measured: three images' stages ran one after the other). */
+typedef std::vector<std::function<void()>> StepList;
+
+void issue_breadth_first(std::vector<StepList> &lists) {
+    size_t longest = 0;
+    for (const StepList &l : lists) longest = std::max(longest, l.size());
+    for (size_t s = 0; s < longest; s++)
+        for (StepList &l : lists) if (s < l.size()) l[s]();
 }
 
-/* Lossless effort-1 encode of few (large) images: every stage but the range coder uses the whole GPU, image after
- * image on the context's stream; the range coders (one warp each) run on a side stream under the stages of the
- * following images (pipe_nblic.cuh).  `idx` = task indices. */
+/* Stable partition of n items by keys[] on scratch set e (pipe_nblic.cuh): e.perm = sorted position -> item, e.sorted =
+ * the items' payload in sorted order; returns where the first position of every key (NKEYS + 1 entries) will be. */
+template <int NKEYS, class T>
+u32 *e1p_sort_steps(nblic_b200_ctx *c, nblic_b200_ctx::E1Set &e, const u32 *keys, const T *payload, long long n, StepList &steps) {
+    const int chunk_items = (int)std::max<long long>(4096, ((n + 255) / 256 + 31) / 32 * 32); /* at most 256 chunks */
+    const int n_chunks = (int)std::max<long long>(1, (n + chunk_items - 1) / chunk_items);
+    u32 *counts = (u32 *)e.counts.p, *key_total = counts + (size_t)kE1NodeKeys * 256, *key_start = key_total + kE1NodeKeys;
+    u32 *perm = (u32 *)e.perm.p;
+    T *sorted = (T *)e.sorted.p;
+    cudaStream_t st = e.st;
+    steps.push_back([=] { psort_count_kernel<NKEYS><<<n_chunks, 256, 0, st>>>(keys, n, chunk_items, n_chunks, counts); });
+    steps.push_back([=] { psort_scan_keys_kernel<<<(NKEYS + 7) / 8, 256, 0, st>>>(counts, NKEYS, n_chunks, key_total); });
+    steps.push_back([=] { psort_scan_totals_kernel<<<1, 1024, 0, st>>>(key_total, NKEYS, key_start); });
+    steps.push_back([=] { psort_scatter_kernel<NKEYS, T><<<n_chunks, 32, 0, st>>>(keys, payload, n, chunk_items, n_chunks, counts, key_start, perm, sorted); });
+    c->launches += 4;
+    return key_start;
+}
+
+/* Lossless effort-1 encode of few (large) images: every stage but the range coder is spread over the whole GPU
+ * (pipe_nblic.cuh).  Up to kE1Sets images are in flight side by side, each on its own stream and scratch set: the stage
+ * kernels of one Kodak-size image occupy a fraction of the machine for a few hundred microseconds each, and the range
+ * coder of an image is a single warp.  Two passes over the group because the number of binary decisions of an image,
+ * which sizes the second half's buffers, comes back from the device in between.  `idx` = task indices. */
 int launch_e1pipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, const std::vector<int> &idx) {
+    using Set = nblic_b200_ctx::E1Set;
     const int n = (int)idx.size();
-    if (!c->side) CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-    if (!c->ev_side) CK(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
-    if ((int)c->e1p_coded.size() < n) c->e1p_coded.resize((size_t)n);
-    CK(c->e1p_counts.reserve(((size_t)kE1NodeKeys * 1024 + kE1NodeKeys + 1) * sizeof(u32)));
-    CK(c->e1p_totals.reserve((size_t)n * 16));
-    CK(c->h_small.reserve(64));
-    CK(cudaMemsetAsync(c->e1p_totals.p, 0, (size_t)n * 16, c->stream));
+    size_t max_px = 1;
+    for (int i : idx) max_px = std::max(max_px, (size_t)tasks[(size_t)i].h * tasks[(size_t)i].w);
+    /* scratch per image in flight: ~70 bytes per pixel; keep the sets inside a 24 GB budget */
+    const int sets = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n, (size_t)nblic_b200_ctx::kE1Sets, ((size_t)24 << 30) / (max_px * 70)}));
+    if ((int)c->e1p.size() < sets) c->e1p.resize((size_t)sets);
+    CK(c->h_small.reserve(sizeof(unsigned long long) * (size_t)sets));
+    unsigned long long *h_total = (unsigned long long *)c->h_small.p;
+    if (!c->ev_e1) CK(cudaEventCreateWithFlags(&c->ev_e1, cudaEventDisableTiming));
+    CK(cudaEventRecord(c->ev_e1, c->stream));
+    for (int k = 0; k < sets; k++) {
+        Set &e = c->e1p[(size_t)k];
+        if (!e.st) CK(cudaStreamCreateWithFlags(&e.st, cudaStreamNonBlocking));
+        if (!e.done) CK(cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming));
+        for (DevBuf *b : e.all) b->st = e.st;
+        CK(cudaStreamWaitEvent(e.st, c->ev_e1, 0)); /* the task table upload */
+        CK(e.counts.reserve(((size_t)kE1NodeKeys * 256 + 2 * kE1NodeKeys + 1) * sizeof(u32)));
+        CK(e.totals.reserve(16));
+    }
     const int wide = c->sm_count * 8;
-    for (int k = 0; k < n; k++) {
-        const Task &t = tasks[(size_t)idx[(size_t)k]];
-        const long long px = (long long)t.h * t.w;
-        const int blocks = (int)std::max<long long>(1, std::min<long long>((px + 255) / 256, wide));
-        unsigned long long *d_total = (unsigned long long *)((uint8_t *)c->e1p_totals.p + (size_t)k * 16);
-        int *d_bad = (int *)(d_total + 1);
-        CK(c->e1p_rec.reserve((size_t)px * 4)); CK(c->e1p_yz.reserve((size_t)px * 4)); CK(c->e1p_doff.reserve((size_t)px * 4));
-        CK(c->e1p_key.reserve((size_t)px * 4)); CK(c->e1p_perm.reserve((size_t)px * 4));
-        u32 *rec = (u32 *)c->e1p_rec.p, *yz = (u32 *)c->e1p_yz.p, *doff = (u32 *)c->e1p_doff.p, *key_start = nullptr;
-        e1p_front_kernel<<<blocks, 256, 0, c->stream>>>(t.src, t.h, t.w, rec, (u32 *)c->e1p_key.p);
-        if (e1p_sort<kE1BiasKeys>(c, (const u32 *)c->e1p_key.p, px, (u32 *)c->e1p_perm.p, &key_start)) return -1;
-        e1p_bias_kernel<<<kE1BiasKeys / 128, 128, 0, c->stream>>>((const u32 *)c->e1p_perm.p, key_start, rec, yz, (u32 *)c->e1p_key.p);
-        if (e1p_sort<kE1RankKeys>(c, (const u32 *)c->e1p_key.p, px, (u32 *)c->e1p_perm.p, &key_start)) return -1;
-        e1p_rank_kernel<<<kE1RankKeys / 64, 64, 0, c->stream>>>((const u32 *)c->e1p_perm.p, key_start, yz);
-        e1p_count_kernel<<<blocks, 256, 0, c->stream>>>(yz, px, t.k_step, doff, d_bad);
-        e1p_scan_kernel<<<1, 1024, 0, c->stream>>>(doff, px, d_total);
-        c->launches += 5;
-        CK(cudaMemcpyAsync(c->h_small.p, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream)); /* the decision count sizes the remaining buffers */
-        const unsigned long long n_dec = *(const unsigned long long *)c->h_small.p;
-        if (n_dec >= (1ull << 31)) { fail(c, "effort-1 pipeline: %llu decisions in one image", n_dec); return -1; }
-        const size_t nv = 2 * (size_t)n_dec;
-        CK(c->e1p_key.reserve(std::max<size_t>(nv, 1) * 4)); CK(c->e1p_perm.reserve(std::max<size_t>(nv, 1) * 4));
-        CK(c->e1p_visrec.reserve(std::max<size_t>(nv, 1))); CK(c->e1p_decrec.reserve(std::max<size_t>(n_dec, 1))); CK(c->e1p_p1.reserve(std::max<size_t>(nv, 1) * 2));
-        CK(c->e1p_coded[(size_t)k].reserve(std::max<size_t>(n_dec, 1) * 2));
-        e1p_emit_kernel<<<blocks, 256, 0, c->stream>>>(yz, px, t.k_step, doff, (u32 *)c->e1p_key.p, (uint8_t *)c->e1p_visrec.p, (uint8_t *)c->e1p_decrec.p);
-        if (e1p_sort<kE1NodeKeys>(c, (const u32 *)c->e1p_key.p, (long long)nv, (u32 *)c->e1p_perm.p, &key_start)) return -1;
-        e1p_node_kernel<<<kE1NodeKeys / 128, 128, 0, c->stream>>>((const u32 *)c->e1p_perm.p, key_start, (const uint8_t *)c->e1p_visrec.p, (uint16_t *)c->e1p_p1.p);
-        const int mix_blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n_dec + 255) / 256, (unsigned long long)wide));
-        e1p_mix_kernel<<<mix_blocks, 256, 0, c->stream>>>((const uint16_t *)c->e1p_p1.p, (const uint8_t *)c->e1p_decrec.p, n_dec, (uint16_t *)c->e1p_coded[(size_t)k].p);
-        c->launches += 3;
-        CK(cudaEventRecord(c->ev_side, c->stream));
-        CK(cudaStreamWaitEvent(c->side, c->ev_side, 0));
-        e1p_coder_kernel<<<1, 32, 0, c->side>>>((Task *)c->tasks.p, idx[(size_t)k], (const uint16_t *)c->e1p_coded[(size_t)k].p, d_total, d_bad);
-        c->launches++;
+    /* NBLIC_B200_E1PIPE_TIMING: per-stage CUDA-event times of the first image on stderr (development aid) */
+    const bool timing = getenv("NBLIC_B200_E1PIPE_TIMING") != nullptr;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    auto mark = [&](int k, const char *name, cudaStream_t st, StepList &steps) {
+        if (!timing || k != 0) return;
+        steps.push_back([&marks, name, st] {
+            cudaEvent_t ev;
+            if (cudaEventCreate(&ev) == cudaSuccess) { cudaEventRecord(ev, st); marks.push_back({name, ev}); }
+        });
+    };
+    Task *d_tasks = (Task *)c->tasks.p;
+    for (int g0 = 0; g0 < n; g0 += sets) {
+        const int cnt = std::min(sets, n - g0);
+        std::vector<StepList> lists((size_t)cnt);
+        for (int k = 0; k < cnt; k++) { /* first half: up to the decision count */
+            Set &e = c->e1p[(size_t)k];
+            StepList &steps = lists[(size_t)k];
+            const Task &t = tasks[(size_t)idx[(size_t)(g0 + k)]];
+            const long long px = (long long)t.h * t.w;
+            const int blocks = (int)std::max<long long>(1, std::min<long long>((px + 255) / 256, wide));
+            const int scan_blocks = (int)((px + kE1ScanBlock - 1) / kE1ScanBlock);
+            CK(e.rec.reserve((size_t)px * 4)); CK(e.yz.reserve((size_t)px * 4)); CK(e.doff.reserve((size_t)px * 4));
+            CK(e.key.reserve((size_t)px * 4)); CK(e.perm.reserve((size_t)px * 4)); CK(e.sorted.reserve((size_t)px * 4));
+            CK(e.sums.reserve((size_t)scan_blocks * 4));
+            u32 *rec = (u32 *)e.rec.p, *yz = (u32 *)e.yz.p, *key = (u32 *)e.key.p, *doff = (u32 *)e.doff.p, *sums = (u32 *)e.sums.p;
+            const u32 *perm = (const u32 *)e.perm.p, *sorted = (const u32 *)e.sorted.p;
+            unsigned long long *d_total = (unsigned long long *)e.totals.p, *h_dst = h_total + k;
+            cudaStream_t st = e.st;
+            const uint8_t *src = t.src;
+            const int h = t.h, w = t.w, k_step = t.k_step;
+            steps.push_back([=] { cudaMemsetAsync(d_total, 0, 16, st); });
+            mark(g0 + k, "start", st, steps);
+            steps.push_back([=] { e1p_front_kernel<<<blocks, 256, 0, st>>>(src, h, w, rec, key); });
+            mark(g0 + k, "front", st, steps);
+            const u32 *ks_a = e1p_sort_steps<kE1BiasKeys, u32>(c, e, key, rec, px, steps);
+            mark(g0 + k, "sort by bias address", st, steps);
+            steps.push_back([=] { e1p_bias_kernel<<<kE1BiasKeys / 128, 128, 0, st>>>(perm, sorted, ks_a, yz, key); });
+            mark(g0 + k, "bias chains", st, steps);
+            const u32 *ks_b = e1p_sort_steps<kE1RankKeys, u32>(c, e, key, yz, px, steps);
+            mark(g0 + k, "sort by rank key", st, steps);
+            steps.push_back([=] { e1p_rank_kernel<<<kE1RankKeys / 64, 64, 0, st>>>(perm, sorted, ks_b, yz); });
+            mark(g0 + k, "rank chains", st, steps);
+            steps.push_back([=] { e1p_count_kernel<<<scan_blocks, 256, 0, st>>>(yz, px, k_step, doff, sums, (int *)(d_total + 1)); });
+            steps.push_back([=] { e1p_scan_kernel<<<1, 1024, 0, st>>>(sums, scan_blocks, d_total); });
+            mark(g0 + k, "count + scan decisions", st, steps);
+            steps.push_back([=] { cudaMemcpyAsync(h_dst, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st); });
+            c->launches += 5;
+        }
+        issue_breadth_first(lists);
+        CK(cudaGetLastError());
+        for (StepList &l : lists) l.clear();
+        for (int k = 0; k < cnt; k++) { /* second half: the decision count sizes the remaining buffers */
+            Set &e = c->e1p[(size_t)k];
+            StepList &steps = lists[(size_t)k];
+            const int ti = idx[(size_t)(g0 + k)];
+            const Task &t = tasks[(size_t)ti];
+            const long long px = (long long)t.h * t.w;
+            const int blocks = (int)std::max<long long>(1, std::min<long long>((px + 255) / 256, wide));
+            CK(cudaStreamSynchronize(e.st));
+            const unsigned long long n_dec = h_total[k];
+            if (n_dec >= (1ull << 31)) { fail(c, "effort-1 pipeline: %llu decisions in one image", n_dec); return -1; }
+            const size_t nv = std::max<size_t>(2 * (size_t)n_dec, 1);
+            CK(e.key.reserve(nv * 4)); CK(e.perm.reserve(nv * 4)); CK(e.sorted.reserve(nv));
+            CK(e.visrec.reserve(nv)); CK(e.decrec.reserve(nv / 2 + 1)); CK(e.p1.reserve(nv * 2)); CK(e.coded.reserve(nv + 2));
+            const u32 *yz = (const u32 *)e.yz.p, *doff = (const u32 *)e.doff.p, *sums = (const u32 *)e.sums.p, *perm = (const u32 *)e.perm.p;
+            u32 *key = (u32 *)e.key.p;
+            uint8_t *visrec = (uint8_t *)e.visrec.p, *decrec = (uint8_t *)e.decrec.p;
+            const uint8_t *sorted = (const uint8_t *)e.sorted.p;
+            uint16_t *p1 = (uint16_t *)e.p1.p, *coded = (uint16_t *)e.coded.p;
+            const unsigned long long *d_total = (const unsigned long long *)e.totals.p;
+            cudaStream_t st = e.st;
+            const int k_step = t.k_step;
+            steps.push_back([=] { e1p_emit_kernel<<<blocks, 256, 0, st>>>(yz, px, k_step, doff, sums, key, visrec, decrec); });
+            mark(g0 + k, "emit visits", st, steps);
+            const u32 *ks = e1p_sort_steps<kE1NodeKeys, uint8_t>(c, e, key, visrec, 2 * (long long)n_dec, steps);
+            mark(g0 + k, "sort visits by node", st, steps);
+            steps.push_back([=] { e1p_node_kernel<<<kE1NodeKeys / 128, 128, 0, st>>>(perm, sorted, ks, p1); });
+            mark(g0 + k, "node chains", st, steps);
+            const int mix_blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n_dec + 255) / 256, (unsigned long long)wide));
+            steps.push_back([=] { e1p_mix_kernel<<<mix_blocks, 256, 0, st>>>(p1, decrec, n_dec, coded); });
+            mark(g0 + k, "mix", st, steps);
+            steps.push_back([=] { e1p_coder_kernel<<<1, 32, 0, st>>>(d_tasks, ti, coded, d_total, (const int *)(d_total + 1)); });
+            mark(g0 + k, "range coder", st, steps);
+            c->launches += 4;
+        }
+        issue_breadth_first(lists);
         CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(c->ev_side, c->side));
-    CK(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
+    if (timing && !marks.empty()) {
+        cudaDeviceSynchronize();
+        for (size_t m = 1; m < marks.size(); m++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[m - 1].second, marks[m].second);
+            fprintf(stderr, "e1pipe %-24s %8.3f ms\n", marks[m].first, ms);
+        }
+        for (auto &m : marks) cudaEventDestroy(m.second);
+    }
+    for (int k = 0; k < sets; k++) { /* the context's stream continues when every image is coded */
+        CK(cudaEventRecord(c->e1p[(size_t)k].done, c->e1p[(size_t)k].st));
+        CK(cudaStreamWaitEvent(c->stream, c->e1p[(size_t)k].done, 0));
+    }
     return 0;
 }
 
@@ -439,13 +565,13 @@ int run_tasks(nblic_b200_ctx *c, std::vector<Task> &tasks) {
         switch (g) {
             case G_Q:
                 /* few images: one warp per image would leave the GPU empty and the front end on the critical path */
-                if (!DEC && coop_ok && (c->qpipe == 1 || (c->qpipe != 0 && cnt <= 64))) { rc = launch_qpipe_encode(c, tasks, group[g], d_ord); pipelined = true; }
+                if (!DEC && coop_ok && (c->qpipe == 1 || (c->qpipe != 0 && cnt <= 8 && c->co_streams == 0))) /* measured cross-over on Kodak-size images: ~10 */ { rc = launch_qpipe_encode(c, tasks, group[g], d_ord); pipelined = true; }
                 else rc = coop_ok ? launch_coop_q<DEC>(c, cnt, d_ord, d_q) : launch_coder<KIND_Q, DEC>(c, cnt, d_ord, d_q, 1, 0);
                 break;
             case G_SEQ: rc = launch_coder<KIND_N, DEC>(c, cnt, d_ord, d_q, max_w[g], seq_effort); break;
             case G_E1_LOSSLESS:
                 /* few images: the stages of every image spread over the whole GPU, only the range coders are one warp each */
-                if (c->e1pipe == 1 || (c->e1pipe != 0 && cnt <= 128 && c->co_streams == 0)) { rc = launch_e1pipe_encode(c, tasks, group[g]); pipelined = true; }
+                if (c->e1pipe == 1 || (c->e1pipe != 0 && cnt <= 64 && c->co_streams == 0)) /* measured cross-over: ~90 images (24 Kodak-size images: 84 ms against 213 ms) */ { rc = launch_e1pipe_encode(c, tasks, group[g]); pipelined = true; }
                 else rc = launch_coop<0, 0>(c, cnt, d_ord, d_q, max_w[g], max_nodes[g]);
                 break;
             case G_FB1:
@@ -494,6 +620,9 @@ size_t nblic_b200_stream_bound(int height, int width) {
 }
 
 nblic_b200_ctx *nblic_b200_create(int device) {
+    /* Concurrent streams (host lanes, the single-image pipelines) map onto the device's hardware work queues: 8 by
+     * default, 32 at most.  Only effective when this is the process's first CUDA call; never overrides the caller's choice. */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) { fail(nullptr, "no CUDA device: %s", cudaGetErrorString(e)); return nullptr; }
@@ -513,6 +642,12 @@ nblic_b200_ctx *nblic_b200_create(int device) {
     }
     if (prop.major < 10) { fail(nullptr, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor); delete c; return nullptr; }
     c->sm_count = prop.multiProcessorCount;
+    for (DevBuf *b : all_buffers(c)) b->st = c->stream;
+    { /* keep released scratch in the device's allocation pool instead of handing it back at every synchronisation */
+        cudaMemPool_t pool;
+        uint64_t keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     return c;
 }
 
@@ -522,14 +657,15 @@ void nblic_b200_destroy(nblic_b200_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy) cudaStreamSynchronize(c->copy);
-    DevBuf *bufs[] = {&c->tasks, &c->order, &c->queue, &c->slots, &c->sym, &c->cold, &c->coop_counts, &c->sub_scratch, &c->pipe_meta, &c->pipe_sorted, &c->pipe_counts, &c->avp, &c->offsets, &c->flags, &c->pixels, &c->streams, &c->recon, &c->peeks};
-    for (DevBuf *b : bufs) b->release();
-    DevBuf *more[] = {&c->e1p_rec, &c->e1p_key, &c->e1p_perm, &c->e1p_counts, &c->e1p_yz, &c->e1p_doff, &c->e1p_visrec, &c->e1p_decrec, &c->e1p_p1, &c->e1p_totals};
-    for (DevBuf *b : more) b->release();
-    for (DevBuf &b : c->e1p_coded) b.release();
+    for (DevBuf *b : all_buffers(c)) b->release();
+    for (nblic_b200_ctx::E1Set &e : c->e1p) {
+        for (DevBuf *b : e.all) b->release();
+        if (e.st) { cudaStreamSynchronize(e.st); cudaStreamDestroy(e.st); }
+        if (e.done) cudaEventDestroy(e.done);
+    }
+    if (c->ev_e1) cudaEventDestroy(c->ev_e1);
+    if (c->stream) cudaStreamSynchronize(c->stream); /* the stream-ordered frees */
     c->h_tasks.release(); c->h_order.release(); c->h_small.release();
-    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
-    if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_copy) if (e) cudaEventDestroy(e);

@@ -6,6 +6,11 @@ import sys
 import numpy as np
 import pytest
 
+# Every kernel of the library is loaded when CUDA initialises: with lazy loading the first launch of a kernel may wait
+# for running kernels of other streams, and test_gpu_parity.py keeps a minutes-long single-image launch running under
+# the other tests (named_configs_job).
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
