@@ -17,7 +17,7 @@
  *                        scan = position of every decision in the stream), then emitted as two counter-node VISITS
  *                        each (main / side class)                                                 R: NBLIC.c:640-679
  *   [stable partition of the visits by counter node: 16 x 256 keys]
- *   e1p_node_kernel      lane per counter node, its visits in decision order: P(1), learn         R: NBLIC.c:589-617
+ *   e1p_node_kernel      warp per counter node, its visits in decision order: P(1), learn         R: NBLIC.c:589-617
  *   e1p_mix_kernel       lane per decision: mixed probability | bit << 12                         R: NBLIC.c:620-637
  *   e1p_coder_kernel     one warp per image: the range coder, the only serial stage               R: NBLIC.c:527-586
  *
@@ -335,36 +335,38 @@ __global__ void __launch_bounds__(256) e1p_emit_kernel(const u32 *yz, long long 
 }
 
 /* ---- stage 5: counter-node chains ------------------------------------------------------------------------- */
-/* One lane per node; p1[visit] = floor(4096 n1 / (n0 + n1)) before the visit's update. */
+/* One WARP per node (a few nodes -- the first unary decision of the common classes -- own a tenth of all visits each, so
+ * the longest chain sets the stage's time): the lanes load 32 visits coalesced, every lane runs the 32-step counter chain
+ * (uniform: six dependent operations a visit, the visits' records arrive by shuffles issued eight ahead), lane u keeps the
+ * counter pair visit u sees, and the 32 probabilities floor(4096 n1 / (n0 + n1)) are then computed and stored side by side. */
 __global__ void __launch_bounds__(128) e1p_node_kernel(const u32 *perm, const uint8_t *sorted_rec, const u32 *key_start, uint16_t *p1) {
-    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (node >= kE1NodeKeys) return;
     const u32 lo = key_start[node], hi = key_start[node + 1];
     u32 c = (u32)N_MIX | ((u32)N_MIX << 16);
-    ChainBatch<uint8_t> cur, nxt;
-    chain_load(cur, perm, sorted_rec, lo, hi);
-    for (u32 base = lo; base < hi; base += 8) {
-        chain_load(nxt, perm, sorted_rec, base + 8, hi);
-        u32 before[8]; /* the counter pair each visit sees */
+    for (u32 base = lo; base < hi; base += 32) {
+        const bool mine = base + lane < hi;
+        const u32 my_idx = mine ? __ldg(perm + base + lane) : 0u;
+        const u32 my_rec = mine ? (u32)__ldg(sorted_rec + base + lane) : 0u; /* a record of 0 (weight 0) leaves the pair alone */
+        u32 seen = c;
 #pragma unroll
-        for (int u = 0; u < 8; u++) { /* the chain proper: six dependent operations a visit */
-            before[u] = c;
-            if (base + u < hi) {
-                const u32 r = cur.rec[u];
-                const int bit = (int)(r & 1u), weight = (int)((r >> 1) & 63u);
+        for (int g = 0; g < 32; g += 8) {
+            u32 r[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) r[k] = __shfl_sync(FULL, my_rec, g + k);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (lane == g + k) seen = c;
+                const int bit = (int)(r[k] & 1u), weight = (int)((r[k] >> 1) & 63u);
                 c = learn_packed(c, pair_sum(c), bit, weight);
-                if (r & 0x80u) c = learn_packed(c, pair_sum(c), bit, N_MIX - weight); /* both classes are this node: it learns the side weight too (R: NBLIC.c:633-636) */
+                if (r[k] & 0x80u) c = learn_packed(c, pair_sum(c), bit, N_MIX - weight); /* both classes are this node: it learns the side weight too (R: NBLIC.c:633-636) */
             }
         }
-#pragma unroll
-        for (int u = 0; u < 8; u++) { /* the eight probabilities are independent of each other: they pipeline */
-            if (base + u < hi) {
-                const uint16_t p = (uint16_t)node_p1_fast(before[u], pair_sum(before[u]));
-                p1[cur.idx[u]] = p;
-                if (cur.rec[u] & 0x80u) p1[cur.idx[u] + 1] = p;
-            }
+        if (mine) {
+            const uint16_t p = (uint16_t)node_p1_fast(seen, pair_sum(seen));
+            p1[my_idx] = p;
+            if (my_rec & 0x80u) p1[my_idx + 1] = p;
         }
-        cur = nxt;
     }
 }
 

@@ -121,7 +121,7 @@ struct nblic_b200_ctx {
     std::vector<E1Set> e1p;
     cudaEvent_t ev_e1 = nullptr; /* marks the task-table upload for the sets' streams */
     int occ_warp[2] = {0, 0};
-    nblic_b200_ctx *lane[4] = {nullptr, nullptr, nullptr, nullptr}; /* host-buffer calls: sub-contexts coding the pieces of a batch side by side (see split_over_lanes) */
+    nblic_b200_ctx *lane[8] = {}; /* host-buffer calls: sub-contexts coding the pieces of a batch side by side (see split_over_lanes) */
 };
 
 namespace {
@@ -264,23 +264,45 @@ int launch_qpipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, const
     CK(cudaMemsetAsync(c->coop_counts.p, 0, (size_t)n * Q_TAB_ENTRIES * sizeof(u32), c->stream));
     u32 *meta = (u32 *)c->pipe_meta.p, *counts = (u32 *)c->pipe_counts.p, *key_start = counts + max_counts;
     uint2 *sorted = (uint2 *)c->pipe_sorted.p;
+    const bool timing = getenv("NBLIC_B200_E1PIPE_TIMING") != nullptr; /* development aid: stage times of the first image on stderr */
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    auto mark = [&](int k, const char *name) {
+        if (!timing || k != 0) return;
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) == cudaSuccess) { cudaEventRecord(ev, c->stream); marks.push_back({name, ev}); }
+    };
     for (int k = 0; k < n; k++) {
         const Task &t = tasks[(size_t)idx[(size_t)k]];
         const long long px = (long long)t.h * t.w;
         int chunk_px, n_chunks;
         chunking((size_t)px, chunk_px, n_chunks);
         const int front_blocks = 1 + (int)std::max<long long>(1, std::min<long long>((px + 255) / 256, (long long)c->sm_count * 8));
+        mark(k, "start");
         qpipe_front_kernel<<<front_blocks, 256, 0, c->stream>>>(t.src, t.h, t.w, meta);
+        mark(k, "front");
         qpipe_count_kernel<<<n_chunks, 256, 0, c->stream>>>(meta, px, chunk_px, n_chunks, counts);
         qpipe_scan_kernel<<<1, 1024, 0, c->stream>>>(counts, n_chunks, key_start);
         qpipe_scatter_kernel<<<n_chunks, 32, 0, c->stream>>>(meta, px, chunk_px, n_chunks, counts, sorted);
+        mark(k, "sort by bias address");
         qpipe_chain_kernel<<<(kPipeKeys + 127) / 128, 128, 0, c->stream>>>(sorted, key_start, reinterpret_cast<uint16_t *>(t.sym),
                                                                          (u32 *)c->coop_counts.p + (size_t)k * Q_TAB_ENTRIES);
+        mark(k, "bias chains");
         c->launches += 5;
     }
+    mark(0, "other images");
     qpipe_finish_kernel<<<n, 32, 0, c->stream>>>((Task *)c->tasks.p, d_order, n, (u32 *)c->coop_counts.p);
+    mark(0, "histograms + rANS sweep");
     c->launches++;
     CK(cudaGetLastError());
+    if (timing && !marks.empty()) {
+        cudaDeviceSynchronize();
+        for (size_t m = 1; m < marks.size(); m++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[m - 1].second, marks[m].second);
+            fprintf(stderr, "qpipe %-24s %8.3f ms\n", marks[m].first, ms);
+        }
+        for (auto &m : marks) cudaEventDestroy(m.second);
+    }
     return 0;
 }
 
@@ -418,7 +440,7 @@ int launch_e1pipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, cons
             mark(g0 + k, "emit visits", st, steps);
             const u32 *ks = e1p_sort_steps<kE1NodeKeys, uint8_t>(c, e, key, visrec, 2 * (long long)n_dec, steps);
             mark(g0 + k, "sort visits by node", st, steps);
-            steps.push_back([=] { e1p_node_kernel<<<kE1NodeKeys / 128, 128, 0, st>>>(perm, sorted, ks, p1); });
+            steps.push_back([=] { e1p_node_kernel<<<kE1NodeKeys / 4, 128, 0, st>>>(perm, sorted, ks, p1); });
             mark(g0 + k, "node chains", st, steps);
             const int mix_blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n_dec + 255) / 256, (unsigned long long)wide));
             steps.push_back([=] { e1p_mix_kernel<<<mix_blocks, 256, 0, st>>>(p1, decrec, n_dec, coded); });
@@ -1007,11 +1029,11 @@ static int decode_batch_one_lane(nblic_b200_ctx *c, int n, const uint8_t *const 
 /*
  * Host-buffer calls on batches of more than kLaneMinImagesPerSm images per SM.  One lane = upload a piece, code it,
  * download it, all on its own streams and scratch (a sub-context driven by its own host thread).  The batch is cut into
- * up to four pieces, one per lane, and the lanes run side by side: the pieces' kernels are co-resident, so the SMs see
+ * up to eight pieces, one per lane, and the lanes run side by side: the pieces' kernels are co-resident, so the SMs see
  * the same number of coder streams as one launch over the whole batch would give them (the coder kernels are
  * latency-bound: their throughput is set by the resident streams), while the upload of piece k+1 rides under the
  * kernels of pieces <= k and the download of piece k under those of pieces > k.  Exposed PCIe time: the first
- * upload and the last download, i.e. about half of the traffic of ONE piece.
+ * upload and the last download, i.e. the traffic of ONE piece (an eighth of the batch).
  * (Round 2 first tried two lanes taking alternate pieces of 24 images per SM: each launch then held a quarter of the
  * streams the 4-streams-per-warp decoder needs to fill the machine, and the end-to-end rate FELL to 0.53 of the
  * device-resident one.)
@@ -1034,7 +1056,7 @@ static int split_over_lanes(nblic_b200_ctx *c, int n, Piece piece) {
         l->coder_ms_total = 0.f;
         l->co_streams = n;
     }
-    int result[kLanes] = {0, 0, 0, 0};
+    int result[kLanes] = {};
     auto work = [&](int who) {
         for (int k = who; k < n_pieces; k += lanes) {
             const int lo = k * piece_n, cnt = std::min(n - lo, piece_n);
