@@ -38,6 +38,10 @@ import time
 
 import numpy as np
 
+# More hardware work queues than the default 8 (must be set before CUDA initialises): the streams of the host lanes and
+# of the single-image pipelines then get a queue each.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

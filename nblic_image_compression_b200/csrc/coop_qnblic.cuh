@@ -148,6 +148,18 @@ __device__ bool coop_q_encode(const uint8_t *img, int h, int w, uint16_t *out, u
     return coop_q_finish(sym, h, w, out, cap, tab, lane, head_words, tail_words);
 }
 
+/* Per-stream symbol statistics in global memory: Q_TAB_ENTRIES counters (then freq | cumulative << 16), followed by the
+ * Q_TAB_ENTRIES division magics of pass 2. */
+constexpr int Q_TAB_STRIDE = 2 * Q_TAB_ENTRIES;
+
+/* Exact floor(n / f) for every 32-bit n by one multiply-high (round-up method, Granlund & Montgomery): with
+ * l = ceil(log2 f) and magic = floor(2^32 (2^l - f) / f) + 1,  t = mulhi(magic, n),  q = (t + ((n - t) >> min(l, 1))) >> max(l - 1, 0).
+ * A power of two (f = 1 included) gives magic = 1, t = 0 and the plain shift. */
+NB_DEV u32 q_div_magic(u32 f) {
+    const int l = f > 1 ? 32 - __clz((int)(f - 1)) : 0;
+    return (u32)(((u64)((1u << l) - f) << 32) / f) + 1u;
+}
+
 /* Second half of the encoder: header, the 12 histogram descriptions, and pass 2 (the reverse rANS sweep) over the
  * (class | y << 8) symbols of pass 1 and their counts in `tab`.  One warp; also the final stage of the
  * whole-GPU single-image pipeline (pipe_qnblic.cuh). */
@@ -156,19 +168,40 @@ __device__ bool coop_q_finish(const uint16_t *sym, int h, int w, uint16_t *out, 
     if (lane == 0) { out[0] = 0x3051; out[1] = 0x322e; out[2] = (uint16_t)h; out[3] = (uint16_t)w; } /* R: QNBLIC.c:463-473 */
     const u32 o = q_finish_histograms(tab, out, 4, cap, lane);
     if (o >= cap) return false;
+    u32 *magic = tab + Q_TAB_ENTRIES;
+    for (int k = lane; k < Q_TAB_ENTRIES; k += 32) { const u32 f = tab[k] & 0xffffu; magic[k] = f ? q_div_magic(f) : 0u; }
+    __syncwarp();
 
-    /* pass 2: rANS, last pixel first, words written downwards from the end of the slot.  R: QNBLIC.c:238-253,635-650 */
+    /* pass 2: rANS, last pixel first, words written downwards from the end of the slot.  R: QNBLIC.c:238-253,635-650.
+     * This sweep is the one serial chain of the encoder and its warp issues an instruction every ~5 cycles, so what
+     * counts is the number of DEPENDENT operations per symbol: state / freq is one multiply-high and two shift-adds with
+     * the entry's magic (exact: no correction steps), everything that does not depend on the state -- the block's table
+     * entries (fetched one block ahead), shuffles (eight symbols ahead), shift counts -- sits off the chain. */
     u32 state = 1u << 16, p = cap;
     bool ok = true;
     const long long n = (long long)h * w;
-    auto fetch = [&](long long base, u32 &e, u32 &m) { /* (freq | cumulative << 16, reciprocal) of the block's 32 symbols */
+    auto fetch = [&](long long base, u32 &e, u32 &m) { /* (freq | cumulative << 16, magic) of the block's 32 symbols */
         const long long idx = base + lane;
-        e = 1u; m = 0u;
+        e = 1u; m = 1u;
         if (base >= 0 && idx < n) {
             const u32 pair = (u32)sym[idx];
-            e = __ldcg(tab + (pair & 255u) * 256 + (pair >> 8));
-            m = 0xffffffffu / max(e & 0xffffu, 1u); /* floor((2^32 - 1) / freq): quotient estimate low by at most 2 */
+            const u32 at = (pair & 255u) * 256 + (pair >> 8);
+            e = __ldcg(tab + at);
+            m = __ldcg(magic + at);
         }
+    };
+    auto step = [&](u32 ej, u32 mj) {
+        const u32 f = ej & 0xffffu, cum = ej >> 16;
+        const int l = 32 - __clz((int)(f - 1)), sh1 = min(l, 1), sh2 = l - sh1; /* f >= 1; clz(0) = 32 gives l = 0 */
+        u32 t = __umulhi(state, mj);
+        u32 q = (t + ((state - t) >> sh1)) >> sh2;
+        if (q > 0x1ffffu) {
+            if (p > o) { p--; if (lane == 0) out[p] = (uint16_t)state; } else ok = false;
+            state >>= 16;
+            t = __umulhi(state, mj);
+            q = (t + ((state - t) >> sh1)) >> sh2;
+        }
+        state = (state - q * f) + (q << Q_NORM_BITS) + cum;
     };
     u32 e, m, e_next, m_next;
     long long base = ((n - 1) / 32) * 32;
@@ -176,22 +209,7 @@ __device__ bool coop_q_finish(const uint16_t *sym, int h, int w, uint16_t *out, 
     for (; base >= 0; base -= 32) {
         fetch(base - 32, e_next, m_next); /* one block ahead: the L2 latency hides behind the 32 coder steps */
         const int last = (int)min(31ll, n - 1 - base);
-        auto step = [&](u32 ej, u32 mj) {
-            const u32 f = ej & 0xffffu, cum = ej >> 16;
-            u32 q = __umulhi(state, mj), r = state - q * f;
-            if (r >= f) { q++; r -= f; }
-            if (r >= f) { q++; r -= f; }
-            if (q > 0x1ffffu) {
-                if (p > o) { p--; if (lane == 0) out[p] = (uint16_t)state; } else ok = false;
-                state >>= 16;
-                q = __umulhi(state, mj); r = state - q * f;
-                if (r >= f) { q++; r -= f; }
-                if (r >= f) { q++; r -= f; }
-            }
-            state = r + (q << Q_NORM_BITS) + cum;
-        };
-        if (last == 31) { /* the shuffles of eight symbols are issued ahead of their eight state updates (a shuffle pair in
-                           * front of every update kept ~25 cycles of latency on the chain) */
+        if (last == 31) {
             for (int g = 24; g >= 0; g -= 8) {
                 u32 ee[8], mm[8];
 #pragma unroll

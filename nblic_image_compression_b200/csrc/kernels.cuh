@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(32) coop_q_kernel(Task *tasks, const int *orde
         else {
             u32 head = 0, tail = 0;
             const bool ok = coop_q_encode(t.src, t.h, t.w, reinterpret_cast<uint16_t *>(t.slot), t.slot_cap / 2, t.sym, sm,
-                                          tabs + (size_t)blockIdx.x * Q_TAB_ENTRIES, lane, head, tail);
+                                          tabs + (size_t)blockIdx.x * Q_TAB_STRIDE, lane, head, tail);
             if (lane == 0) {
                 if (ok) { t.head_len = head * 2; t.tail_len = tail * 2; }
                 else { t.status = NBLIC_B200_OVERFLOW; t.head_len = t.tail_len = 0; }
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(32) qpipe_finish_kernel(Task *tasks, const int
     Task &t = tasks[order[blockIdx.x]];
     u32 head = 0, tail = 0;
     const bool ok = coop_q_finish(reinterpret_cast<const uint16_t *>(t.sym), t.h, t.w, reinterpret_cast<uint16_t *>(t.slot), t.slot_cap / 2,
-                                  tabs + (size_t)blockIdx.x * Q_TAB_ENTRIES, lane, head, tail);
+                                  tabs + (size_t)blockIdx.x * Q_TAB_STRIDE, lane, head, tail);
     if (lane == 0) {
         if (ok) { t.head_len = head * 2; t.tail_len = tail * 2; }
         else { t.status = NBLIC_B200_OVERFLOW; t.head_len = t.tail_len = 0; }

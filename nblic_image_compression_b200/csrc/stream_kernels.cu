@@ -121,7 +121,7 @@ struct nblic_b200_ctx {
     std::vector<E1Set> e1p;
     cudaEvent_t ev_e1 = nullptr; /* marks the task-table upload for the sets' streams */
     int occ_warp[2] = {0, 0};
-    nblic_b200_ctx *lane[8] = {}; /* host-buffer calls: sub-contexts coding the pieces of a batch side by side (see split_over_lanes) */
+    nblic_b200_ctx *lane[4] = {}; /* host-buffer calls: sub-contexts coding the pieces of a batch side by side (see split_over_lanes) */
 };
 
 namespace {
@@ -204,7 +204,7 @@ int launch_coop_q(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_que
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_q_kernel<DEC>, 32, 0));
     const int grid = balanced_grid(n_order, c->sm_count * std::max(per_sm, 1));
-    if (!DEC) CK(c->coop_counts.reserve((size_t)grid * Q_TAB_ENTRIES * sizeof(u32))); /* encoder: per-CTA symbol statistics in L2 */
+    if (!DEC) CK(c->coop_counts.reserve((size_t)grid * Q_TAB_STRIDE * sizeof(u32))); /* encoder: per-CTA symbol statistics in L2 */
     coop_q_kernel<DEC><<<grid, 32, 0, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (u32 *)c->coop_counts.p);
     c->launches++;
     CK(cudaGetLastError());
@@ -260,8 +260,8 @@ int launch_qpipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, const
     CK(c->pipe_meta.reserve(max_px * sizeof(u32)));
     CK(c->pipe_sorted.reserve(max_px * sizeof(uint2)));
     CK(c->pipe_counts.reserve((max_counts + kPipeKeys + 1) * sizeof(u32)));
-    CK(c->coop_counts.reserve((size_t)n * Q_TAB_ENTRIES * sizeof(u32)));
-    CK(cudaMemsetAsync(c->coop_counts.p, 0, (size_t)n * Q_TAB_ENTRIES * sizeof(u32), c->stream));
+    CK(c->coop_counts.reserve((size_t)n * Q_TAB_STRIDE * sizeof(u32)));
+    CK(cudaMemsetAsync(c->coop_counts.p, 0, (size_t)n * Q_TAB_STRIDE * sizeof(u32), c->stream));
     u32 *meta = (u32 *)c->pipe_meta.p, *counts = (u32 *)c->pipe_counts.p, *key_start = counts + max_counts;
     uint2 *sorted = (uint2 *)c->pipe_sorted.p;
     const bool timing = getenv("NBLIC_B200_E1PIPE_TIMING") != nullptr; /* development aid: stage times of the first image on stderr */
@@ -285,7 +285,7 @@ int launch_qpipe_encode(nblic_b200_ctx *c, const std::vector<Task> &tasks, const
         qpipe_scatter_kernel<<<n_chunks, 32, 0, c->stream>>>(meta, px, chunk_px, n_chunks, counts, sorted);
         mark(k, "sort by bias address");
         qpipe_chain_kernel<<<(kPipeKeys + 127) / 128, 128, 0, c->stream>>>(sorted, key_start, reinterpret_cast<uint16_t *>(t.sym),
-                                                                         (u32 *)c->coop_counts.p + (size_t)k * Q_TAB_ENTRIES);
+                                                                         (u32 *)c->coop_counts.p + (size_t)k * Q_TAB_STRIDE);
         mark(k, "bias chains");
         c->launches += 5;
     }
@@ -1029,11 +1029,11 @@ static int decode_batch_one_lane(nblic_b200_ctx *c, int n, const uint8_t *const 
 /*
  * Host-buffer calls on batches of more than kLaneMinImagesPerSm images per SM.  One lane = upload a piece, code it,
  * download it, all on its own streams and scratch (a sub-context driven by its own host thread).  The batch is cut into
- * up to eight pieces, one per lane, and the lanes run side by side: the pieces' kernels are co-resident, so the SMs see
+ * up to four pieces, one per lane, and the lanes run side by side: the pieces' kernels are co-resident, so the SMs see
  * the same number of coder streams as one launch over the whole batch would give them (the coder kernels are
  * latency-bound: their throughput is set by the resident streams), while the upload of piece k+1 rides under the
  * kernels of pieces <= k and the download of piece k under those of pieces > k.  Exposed PCIe time: the first
- * upload and the last download, i.e. the traffic of ONE piece (an eighth of the batch).
+ * upload and the last download, i.e. the traffic of ONE piece (a quarter of the batch).
  * (Round 2 first tried two lanes taking alternate pieces of 24 images per SM: each launch then held a quarter of the
  * streams the 4-streams-per-warp decoder needs to fill the machine, and the end-to-end rate FELL to 0.53 of the
  * device-resident one.)
@@ -1045,6 +1045,8 @@ constexpr int kLanePieceMax = 16384; /* bounds the per-lane scratch; larger batc
 
 template <class Piece>
 static int split_over_lanes(nblic_b200_ctx *c, int n, Piece piece) {
+    /* Four lanes: eight (pieces of 1250 images on configs[4]) measured 0.58 of the device-resident rate end to end
+     * against 0.95 with four, with 8 or 32 hardware work queues alike. */
     constexpr int kLanes = (int)(sizeof c->lane / sizeof c->lane[0]);
     const int piece_n = std::min(kLanePieceMax, std::max(c->sm_count * 2, (n + kLanes - 1) / kLanes));
     const int n_pieces = (n + piece_n - 1) / piece_n, lanes = std::min(kLanes, n_pieces);

@@ -10,6 +10,7 @@ import pytest
 # for running kernels of other streams, and test_gpu_parity.py keeps a minutes-long single-image launch running under
 # the other tests (named_configs_job).
 os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware work queue per stream of the lanes / single-image pipelines
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
