@@ -20,7 +20,7 @@ _szp = C.POINTER(C.c_size_t)
 _u64p = C.POINTER(C.c_uint64)
 _pp = C.POINTER(C.c_void_p)
 
-MAP_AUTO, MAP_WARP, MAP_LANE = 0, 1, 2
+MAP_AUTO, MAP_WARP, MAP_LANE, MAP_WARP4 = 0, 1, 2, 3
 PIPE_AUTO, PIPE_NEVER, PIPE_ALWAYS = -1, 0, 1
 OK, BAD_DIMS, BAD_HEADER, OVERFLOW, CORRUPT = 0, 1, 2, 3, 4
 

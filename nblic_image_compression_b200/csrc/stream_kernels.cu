@@ -166,7 +166,7 @@ int launch_coder_t(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_qu
 template <int KIND, bool DEC>
 int launch_coder(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, int max_w, int max_effort) {
     int map = c->mapping;
-    if (map == NBLIC_B200_MAP_AUTO) map = MAP_WARP;
+    if (map == NBLIC_B200_MAP_AUTO || map == NBLIC_B200_MAP_WARP4) map = MAP_WARP;
     LaunchPlan plan;
     plan.map = map;
     if (map == MAP_WARP) {
@@ -492,11 +492,15 @@ int launch_subwarp(nblic_b200_ctx *c, int lps, int n_packs, const int *d_packs, 
     return launch_subwarp_t<8, true>(c, n_packs, d_packs, d_queue, max_nodes);
 }
 
-/* Lanes per stream for an effort-1 decode of n streams: several streams per warp pay when the streams outnumber what
- * the one-stream-per-warp kernel keeps resident (issue-bound regime); below that, a stream alone in its warp is faster. */
+/* Lanes per stream for an effort-1 decode of n streams.  Both kernels are latency-bound, so their rate grows with the
+ * streams they hold: four streams per warp run at ~0.27 MPix/s per stream however many there are (10 000 fit), one stream
+ * per warp at 0.53 (21 per SM, full) to 0.85 MPix/s (alone) but at most 21 x SMs at a time -- 1.65 GPix/s.  The packed
+ * kernel wins from about 6 000 streams on (40 per SM). */
 int choose_sub_lps(nblic_b200_ctx *c, int n_streams) {
     if (c->sub_lps == 8 || c->sub_lps == 32) return c->sub_lps;
-    return std::max(n_streams, c->co_streams) >= c->sm_count * 16 ? 8 : 32;
+    if (c->mapping == NBLIC_B200_MAP_WARP4) return 8;
+    if (c->mapping == NBLIC_B200_MAP_WARP) return 32;
+    return std::max(n_streams, c->co_streams) >= c->sm_count * 40 ? 8 : 32;
 }
 
 /* Efforts 2/3 always keep the rank tables in L2.  Effort 1 keeps them in shared memory (lowest latency per
@@ -699,7 +703,7 @@ void nblic_b200_destroy(nblic_b200_ctx *c) {
 const char *nblic_b200_last_error(const nblic_b200_ctx *c) { return c ? c->error.c_str() : g_create_error.c_str(); }
 
 int nblic_b200_set_mapping(nblic_b200_ctx *c, int mapping) {
-    if (!c || mapping < NBLIC_B200_MAP_AUTO || mapping > NBLIC_B200_MAP_LANE) return -1;
+    if (!c || mapping < NBLIC_B200_MAP_AUTO || mapping > NBLIC_B200_MAP_WARP4) return -1;
     c->mapping = mapping;
     for (nblic_b200_ctx *l : c->lane) if (l) l->mapping = mapping;
     return 0;

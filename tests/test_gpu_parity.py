@@ -360,6 +360,31 @@ def test_random_fuzz_vs_checker(api, codec, oracle):
             assert d is not None and np.array_equal(d[0], e[1]), (trial, effort, near, k)
 
 
+def test_packed_effort1_decoder_vs_oracle(api, codec, oracle):
+    """csrc/subwarp_nblic.cuh, the decoder the bench's configs[4] runs on (four effort-1 streams of equal size per warp):
+    forced by MAP_WARP4 on small batches, every near, ragged pack tails (1, 2, 3 streams in the last warp), sizes 1 x 1 up
+    to a few tiles of the staged rows, against the oracle's reconstruction; then garbage behind valid headers."""
+    rng = np.random.default_rng(77)
+    shapes = [(1, 1), (1, 7), (2, 2), (3, 5), (9, 1), (5, 64), (6, 65), (7, 66), (8, 67), (4, 129), (33, 130), (40, 200), (64, 96)]
+    for near in (0, 1, 2, 4, 9):
+        imgs = []
+        for k, (h, w) in enumerate(shapes):
+            for rep in range(1 + (k + near) % 5):  # 1..5 streams of this size: full packs and ragged tails
+                kind = (k + rep) % 3
+                imgs.append(gen(h, w, 100 * k + rep) if kind == 0 else rng.integers(0, 256, size=(h, w), dtype=np.uint8) if kind == 1
+                            else np.full((h, w), (37 * k + rep) % 256, np.uint8))
+        exp = [oracle.n_encode(im, near, 1)[:2] for im in imgs]
+        codec.set_mapping(api.MAP_WARP4)
+        out = codec.decode_batch([e[0] for e in exp])
+        assert codec.last_mapping == "4-streams-per-warp"
+        for k, (d, e) in enumerate(zip(out, exp)):
+            assert d is not None and (d[1], d[2]) == (near, 1) and np.array_equal(d[0], e[1]), (near, k, imgs[k].shape)
+        bad = [e[0][:16] + bytes(rng.integers(0, 256, size=max(len(e[0]) - 16, 1), dtype=np.uint8)) for e in exp[:20]] + [e[0][: 16 + (len(e[0]) - 16) // 2] for e in exp[:20]]
+        res = codec.decode_batch(bad)  # must return: rasters or CORRUPT verdicts, never a fault
+        assert len(res) == len(bad)
+    codec.set_mapping(api.MAP_AUTO)
+
+
 def test_corrupt_streams_never_fault(api, codec):
     """Bit flips, garbage payloads and truncation behind a valid header: the decoders must stay inside
     their buffers and return (a raster or a CORRUPT / BAD_HEADER verdict) -- the reference reads blindly."""
