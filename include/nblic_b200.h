@@ -80,7 +80,8 @@ const char *nblic_b200_last_error(const nblic_b200_ctx *ctx);
 enum {
     NBLIC_B200_MAP_AUTO = 0, /* pick by batch size                                               */
     NBLIC_B200_MAP_WARP = 1, /* one coder stream per warp, adaptive state in shared memory         */
-    NBLIC_B200_MAP_LANE = 2, /* one coder stream per lane, adaptive state in L2/HBM (huge batches) */
+    NBLIC_B200_MAP_LANE = 2, /* one coder stream per lane, the plain sequential formulation: only in the TEST build
+                                (libnblic_b200_seq.so, the parity tests' second opinion); the product library returns -1 */
     NBLIC_B200_MAP_WARP4 = 3 /* as WARP, but the effort-1 decoder packs four streams of equal size into a warp
                                 (csrc/subwarp_nblic.cuh); AUTO picks it from ~40 streams per SM on       */
 };

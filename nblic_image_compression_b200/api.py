@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .build import LIB
+from .build import LIB, LIB_SEQ
 
 _u8p = C.POINTER(C.c_uint8)
 _u16p = C.POINTER(C.c_uint16)
@@ -35,18 +35,19 @@ SYMBOLS = [
     "nblic_b200_launch_count", "nblic_b200_last_coder_ms", "nblic_b200_last_slots", "nblic_b200_last_mapping", "nblic_b200_stream_handle", "nblic_b200_version",
 ]
 
-_lib = None
+_libs = {}
 
 
-def load_library() -> C.CDLL:
-    """Loads libnblic_b200.so; raises if it has not been built (no fallback of any kind)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB):
-        raise RuntimeError(f"{LIB} is missing: run `python -m nblic_image_compression_b200.build` "
+def load_library(sequential: bool = False) -> C.CDLL:
+    """Loads libnblic_b200.so (sequential=True: the test build libnblic_b200_seq.so, which adds the one-agent-per-stream
+    kernels behind MAP_LANE); raises if it has not been built (no fallback of any kind)."""
+    if sequential in _libs:
+        return _libs[sequential]
+    path = LIB_SEQ if sequential else LIB
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -m nblic_image_compression_b200.build` "
                            "(or __graft_entry__.build()); this package has no CPU fallback")
-    lib = C.CDLL(LIB)
+    lib = C.CDLL(path)
     lib.nblic_b200_create.restype = C.c_void_p
     lib.nblic_b200_create.argtypes = [C.c_int]
     lib.nblic_b200_destroy.argtypes = [C.c_void_p]
@@ -81,7 +82,7 @@ def load_library() -> C.CDLL:
     lib.QNBLICcompress.argtypes = [_u16p, _u8p, C.c_int, C.c_int]
     lib.QNBLICcompressMultiThread.argtypes = [_u16p, _u8p, C.c_int, C.c_int]
     lib.QNBLICdecompress.argtypes = [_u16p, _u8p, _ip, _ip]
-    _lib = lib
+    _libs[sequential] = lib
     return lib
 
 
@@ -108,8 +109,8 @@ def _ptr_array(arrs: Sequence[Optional[np.ndarray]]):
 class Codec:
     """One context on one GPU (nblic_b200_create)."""
 
-    def __init__(self, device: int = 0, mapping: int = MAP_AUTO):
-        self.lib = load_library()
+    def __init__(self, device: int = 0, mapping: int = MAP_AUTO, sequential: bool = False):
+        self.lib = load_library(sequential)
         self.ctx = self.lib.nblic_b200_create(device)
         if not self.ctx:
             raise RuntimeError("nblic_b200_create failed: " + self.lib.nblic_b200_last_error(None).decode())

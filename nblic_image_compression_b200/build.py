@@ -36,16 +36,23 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+LIB_SEQ = os.path.join(HERE, "libnblic_b200_seq.so")  # test build: the product + the sequential one-agent-per-stream kernels
+
+
+def build_library(force: bool = False, verbose: bool = False, sequential: bool = False) -> str:
+    """sequential=True builds libnblic_b200_seq.so (-DNBLIC_B200_SEQUENTIAL): the same library plus coder_kernel, the plain
+    sequential formulation the parity tests use as a second implementation (MAP_LANE).  Not part of the product."""
+    lib = LIB_SEQ if sequential else LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES_CU + SOURCES_C]
-    if not force and not _stale(LIB, srcs + HEADERS + [os.path.abspath(__file__)]):
-        return LIB
-    objdir = os.path.join(HERE, "build")
+    if not force and not _stale(lib, srcs + HEADERS + [os.path.abspath(__file__)]):
+        return lib
+    objdir = os.path.join(HERE, "build", "seq" if sequential else "product")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     for s in SOURCES_CU:
         o = os.path.join(objdir, s + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("NBLIC_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [_nvcc(), *NVCC_FLAGS, *(["-DNBLIC_B200_SEQUENTIAL"] if sequential else []), *os.environ.get("NBLIC_NVCC_EXTRA", "").split(),
+               "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
@@ -54,7 +61,9 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(objdir, s + ".o")
         subprocess.run(["gcc", "-O2", "-fPIC", "-Wall", "-Wextra", "-std=gnu99", "-c", os.path.join(CSRC, s), "-o", o], check=True)
         objs.append(o)
-    subprocess.run([_nvcc(), "-shared", "-o", LIB, *objs, "-lpthread", "-cudart", "shared"], check=True)
+    subprocess.run([_nvcc(), "-shared", "-o", lib, *objs, "-lpthread", "-cudart", "shared"], check=True)
+    if sequential:
+        return lib
     subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-std=gnu99", "-o", CLI, os.path.join(CSRC, "nblic_batch_cli.c"),
                     "-L" + HERE, "-lnblic_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
@@ -83,4 +92,5 @@ def build_microbench() -> str:
 
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, sequential=True))
     print(build_microbench())

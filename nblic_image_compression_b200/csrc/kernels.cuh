@@ -4,7 +4,7 @@
  *
  *   coop_nblic_kernel<NAVP, MODE, RG>  warp-cooperative NBLIC, efforts 1-3 (coop_nblic.cuh, coop_avp.cuh)
  *   coop_q_kernel<DEC>                 warp-cooperative QNBLIC, effort 0 (coop_qnblic.cuh)
- *   coder_kernel<KIND, DEC, MAP>       sequential formulation, one agent per stream (codec_core.cuh)
+ *   coder_kernel<KIND, DEC, MAP>       sequential formulation, one agent per stream (codec_core.cuh); test build only (NBLIC_B200_SEQUENTIAL)
  *   scan_lengths_kernel / gather_streams_kernel   compaction of the variable-length streams
  *   peek_headers_kernel, synth_gray_kernel, divcheck_kernel
  */
@@ -50,6 +50,7 @@ constexpr int N_SMEM_BYTES = N_CTX_ENTRIES * 2 + N_FOREST_ENTRIES * 4 + N_RANK_E
 constexpr int N_COUNT_BYTES = N_RANK_ENTRIES * 4;
 constexpr int Q_STATE_BYTES = Q_CTX_ENTRIES * 4 + Q_TAB_ENTRIES * 4; /* 24576 */
 
+#ifdef NBLIC_B200_SEQUENTIAL /* the sequential formulation ships only in the test build (libnblic_b200_seq.so), as the parity tests' second opinion */
 __device__ __forceinline__ NState carve_nstate(uint8_t *hot, uint8_t *counts, i64 *avp, size_t avp_half) {
     NState s;
     s.forest = reinterpret_cast<u32 *>(hot);
@@ -142,6 +143,8 @@ __global__ void __launch_bounds__(32) coder_kernel(Task *tasks, const int *order
         }
     }
 }
+
+#endif /* NBLIC_B200_SEQUENTIAL */
 
 /* Warp-cooperative NBLIC kernels (coop_nblic.cuh, coop_avp.cuh): one warp per CTA, adaptive state in
  * shared memory, rank-mapper frequencies in `counts` (one [512][20] int table per CTA), AVP column

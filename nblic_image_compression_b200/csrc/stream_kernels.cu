@@ -95,7 +95,11 @@ struct nblic_b200_ctx {
     int device = 0;
     int sm_count = 0;
     int mapping = NBLIC_B200_MAP_AUTO;
+#ifdef NBLIC_B200_SEQUENTIAL
     bool serial_only = getenv("NBLIC_B200_SERIAL") != nullptr; /* debugging aid: force the sequential kernels */
+#else
+    bool serial_only = false;
+#endif
     cudaStream_t stream = nullptr, copy = nullptr; /* compute / host<->device copies of the host-buffer calls */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy[2] = {nullptr, nullptr};
     std::string error;
@@ -152,6 +156,7 @@ struct LaunchPlan { int map; int grid; size_t cold_stride; size_t smem; };
  * the resident warps (issue slots are only 62-66 % used), and the dynamic queue already packs the tail.  So: fill. */
 int balanced_grid(int n, int slots) { return std::max(1, std::min(n, slots)); }
 
+#ifdef NBLIC_B200_SEQUENTIAL
 template <int KIND, bool DEC, int MAP>
 int launch_coder_t(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue, const LaunchPlan &plan, size_t avp_stride) {
     auto kern = coder_kernel<KIND, DEC, MAP>;
@@ -198,6 +203,12 @@ int launch_coder(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queu
     if (map == MAP_WARP) return launch_coder_t<KIND, DEC, MAP_WARP>(c, n_order, d_order, d_queue, plan, avp_stride);
     return launch_coder_t<KIND, DEC, MAP_LANE>(c, n_order, d_order, d_queue, plan, avp_stride);
 }
+
+#else
+/* product build: no sequential kernels (they ship in the test build libnblic_b200_seq.so only) */
+template <int KIND, bool DEC>
+int launch_coder(nblic_b200_ctx *c, int, const int *, int *, int, int) { fail(c, "this build carries no sequential kernels (NBLIC_B200_SEQUENTIAL)"); return -1; }
+#endif
 
 template <bool DEC>
 int launch_coop_q(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_queue) {
@@ -638,7 +649,11 @@ void resolve_mode(int near, int effort, int &near_out, int &effort_out) { /* R: 
 
 extern "C" {
 
-const char *nblic_b200_version(void) { return "nblic_b200 0.1 (sm_100a)"; }
+#ifdef NBLIC_B200_SEQUENTIAL
+const char *nblic_b200_version(void) { return "nblic_b200 0.2 (sm_100a, test build with the sequential kernels)"; }
+#else
+const char *nblic_b200_version(void) { return "nblic_b200 0.2 (sm_100a)"; }
+#endif
 
 size_t nblic_b200_stream_bound(int height, int width) {
     if (height <= 0 || width <= 0) return 8192;
@@ -704,6 +719,9 @@ const char *nblic_b200_last_error(const nblic_b200_ctx *c) { return c ? c->error
 
 int nblic_b200_set_mapping(nblic_b200_ctx *c, int mapping) {
     if (!c || mapping < NBLIC_B200_MAP_AUTO || mapping > NBLIC_B200_MAP_WARP4) return -1;
+#ifndef NBLIC_B200_SEQUENTIAL
+    if (mapping == NBLIC_B200_MAP_LANE) { fail(c, "MAP_LANE needs the sequential kernels, which only the test build carries"); return -1; }
+#endif
     c->mapping = mapping;
     for (nblic_b200_ctx *l : c->lane) if (l) l->mapping = mapping;
     return 0;

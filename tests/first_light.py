@@ -11,7 +11,7 @@ from cases import edge_cases, SETTINGS_EDGE
 
 build_oracle()
 orc = Oracle()
-codec = api.Codec(0)
+codec = api.Codec(0, sequential=True)  # test build: also carries the sequential kernels behind MAP_LANE
 
 def oracle_enc(img, effort, near):
     if effort == 0:

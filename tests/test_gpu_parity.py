@@ -28,6 +28,17 @@ def codec(api):
     c.close()
 
 
+@pytest.fixture(scope="module")
+def codec_seq(api):
+    """A context of the TEST build (libnblic_b200_seq.so): the product plus the plain sequential one-agent-per-stream
+    kernels (MAP_LANE) -- an independent second implementation on the GPU that the product library does not ship."""
+    from nblic_image_compression_b200.build import build_library
+    build_library(sequential=True)
+    c = api.Codec(0, sequential=True)
+    yield c
+    c.close()
+
+
 def _oracle_enc(oracle, img, effort, near):
     if effort == 0:
         return oracle.q_encode(img), img
@@ -58,10 +69,10 @@ def _check_batch(api, codec, oracle, images, effort, near, mapping):
 
 
 @pytest.mark.parametrize("effort,near", SETTINGS_EDGE)
-def test_edge_cases_vs_oracle_and_golden(api, codec, oracle, manifest, effort, near):
+def test_edge_cases_vs_oracle_and_golden(api, codec, codec_seq, oracle, manifest, effort, near):
     names, images = zip(*edge_cases())
     for mapping in (api.MAP_WARP, api.MAP_LANE):
-        streams = _check_batch(api, codec, oracle, list(images), effort, near, mapping)
+        streams = _check_batch(api, codec_seq if mapping == api.MAP_LANE else codec, oracle, list(images), effort, near, mapping)
         for name, s in zip(names, streams):
             g = manifest["edge"][name]["streams"][f"e{effort}n{near}"]
             assert len(s) == g["bytes"] and sha(s) == g["sha256"], (name, effort, near)
@@ -462,16 +473,20 @@ def test_full_size_round_trip_properties(api, codec):
     assert (len(s1[1]), sha(s1[1])[:16]) == (7363526, "5a502f759a96971e")
 
 
-def test_lane_mapping_large_batch_matches_warp(api, codec):
+def test_lane_mapping_large_batch_matches_warp(api, codec, codec_seq):
+    """The sequential kernels (test build only) against the product's cooperative ones; the product library refuses MAP_LANE."""
     imgs = [gen(48, 80, s) for s in range(96)]
     codec.set_mapping(api.MAP_WARP)
     a = codec.encode_batch(imgs, 0, 1)[0]
-    codec.set_mapping(api.MAP_LANE)
-    b = codec.encode_batch(imgs, 0, 1)[0]
-    assert a == b and codec.last_mapping == "lane"
-    for im, d in zip(imgs, codec.decode_batch(b)):
-        assert np.array_equal(d[0], im)
+    with pytest.raises(ValueError):
+        codec.set_mapping(api.MAP_LANE)
     codec.set_mapping(api.MAP_AUTO)
+    codec_seq.set_mapping(api.MAP_LANE)
+    b = codec_seq.encode_batch(imgs, 0, 1)[0]
+    assert a == b and codec_seq.last_mapping == "lane"
+    for im, d in zip(imgs, codec_seq.decode_batch(b)):
+        assert np.array_equal(d[0], im)
+    codec_seq.set_mapping(api.MAP_AUTO)
 
 
 def test_decode_overflow_leaves_the_neighbours_alone(api, codec):

@@ -1,4 +1,4 @@
-"""One small batch through encode + decode, for ncu: python tools/profile_case.py N H W EFFORT NEAR [warp|lane] [reps]"""
+"""One small batch through encode + decode, for ncu: python tools/profile_case.py N H W EFFORT NEAR [auto|warp|warp4|lane] [reps]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,7 +6,7 @@ import torch
 from nblic_image_compression_b200 import api
 
 n, h, w, effort, near = (int(x) for x in sys.argv[1:6])
-mapping = {"warp": api.MAP_WARP, "lane": api.MAP_LANE, "auto": api.MAP_AUTO}[sys.argv[6] if len(sys.argv) > 6 else "auto"]
+mapping = {"warp": api.MAP_WARP, "warp4": api.MAP_WARP4, "lane": api.MAP_LANE, "auto": api.MAP_AUTO}[sys.argv[6] if len(sys.argv) > 6 else "auto"]
 reps = int(sys.argv[7]) if len(sys.argv) > 7 else 1
 codec = api.Codec(0, mapping)
 npx = h * w
