@@ -218,6 +218,7 @@ int launch_coop_q(nblic_b200_ctx *c, int n_order, const int *d_order, int *d_que
     if (!DEC) CK(c->coop_counts.reserve((size_t)grid * Q_TAB_STRIDE * sizeof(u32))); /* encoder: per-CTA symbol statistics in L2 */
     coop_q_kernel<DEC><<<grid, 32, 0, c->stream>>>((Task *)c->tasks.p, d_order, n_order, d_queue, (u32 *)c->coop_counts.p);
     c->launches++;
+    c->last_slots = c->sm_count * std::max(per_sm, 1);
     CK(cudaGetLastError());
     return 0;
 }
