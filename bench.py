@@ -215,6 +215,8 @@ def profile_figures(kernel_key):
     k = rec.get("kernels", {}).get(kernel_key)
     if not k:
         return None, "kernel %s not in profiles/r02_ncu.json" % kernel_key
+    if k.get("inst_per_pixel") is None:
+        return None, "ncu could not collect the counters of %s in the capture on record (profiles/r02_ncu.json: %s)" % (kernel_key, k.get("note", "no figures"))
     return k, "ncu --set full capture of this build (git %s, shape %s)" % (rec.get("git_head", "?")[:12], k.get("shape"))
 
 

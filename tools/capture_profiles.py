@@ -40,10 +40,12 @@ METRICS = {
 
 
 def num(x):
+    """A metric as a float; None for missing or not-a-number values (ncu reports nan for counters it could not collect)."""
     try:
-        return float(x.replace(",", ""))
+        v = float(x.replace(",", ""))
     except (ValueError, AttributeError):
         return None
+    return v if v == v and abs(v) != float("inf") else None
 
 
 def main():
