@@ -31,6 +31,35 @@ def test_header_symbols_exported(lib):
         assert getattr(lib, sym) is not None
 
 
+def test_product_and_test_builds(lib):
+    """Two libraries from the same sources: the product carries no sequential kernels (it says so in its version string
+    and its cubin holds no coder_kernel), the test build (-DNBLIC_B200_SEQUENTIAL) does; both export the same ABI."""
+    import subprocess
+    from nblic_image_compression_b200 import api
+    from nblic_image_compression_b200.build import LIB, LIB_SEQ, build_library
+    build_library(sequential=True)
+    seq = api.load_library(sequential=True)
+    assert b"test build" not in lib.nblic_b200_version() and b"test build" in seq.nblic_b200_version()
+    for sym in api.SYMBOLS:
+        assert getattr(seq, sym) is not None
+    names = {path: subprocess.run(["cuobjdump", "-elf", path], capture_output=True, text=True).stdout for path in (LIB, LIB_SEQ)}
+    if names[LIB]:  # cuobjdump present (it is part of the CUDA toolkit of this image)
+        assert "12coder_kernelI" not in names[LIB] and "12coder_kernelI" in names[LIB_SEQ]  # mangled template name (not e1p_coder_kernel)
+        for kernel in ("coop_nblic_kernel", "subwarp_decode_kernel", "coop_q_kernel", "e1p_coder_kernel", "qpipe_finish_kernel", "psort_scatter_kernel"):
+            assert kernel in names[LIB], kernel
+
+
+def test_batch_cli_usage():
+    """nblic_batch (csrc/nblic_batch_cli.c) rejects a bad command line before touching CUDA."""
+    import subprocess
+    from nblic_image_compression_b200.build import CLI, build_library
+    build_library()
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode != 0 and "usage:" in r.stderr and "-b<MiB per group>" in r.stderr
+    r = subprocess.run([CLI, "-cq", "/tmp", "x.pgm"], capture_output=True, text=True)
+    assert r.returncode != 0 and "unknown switch -q" in r.stderr
+
+
 def test_header_is_plain_c(tmp_path):
     """include/nblic_b200.h must be consumable by a C99 compiler (the reference and its CLI are C)."""
     import subprocess
