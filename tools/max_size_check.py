@@ -23,7 +23,8 @@ for effort in (0, 1):
     exp = chk.q_encode(img) if effort == 0 else chk.n_encode(img, 0, 1)[0]
     rec = {"image": f"synthetic {h}x{w} seed 42", "effort": effort, "status": status, "bytes": len(streams[0] or b""), "checker_bytes": len(exp),
            "bit_exact": streams[0] == exp, "encode_s": round(t1 - t0, 1), "checker": chk.name}
-    if effort == 0:
+    rec["encode_mapping"] = codec.last_mapping
+    if effort == 0 and not os.environ.get("NBLIC_SKIP_DECODE"):
         t2 = time.time()
         dec = codec.decode_batch(streams)
         rec["decode_s"] = round(time.time() - t2, 1)
