@@ -60,6 +60,68 @@ def test_batch_cli_usage():
     assert r.returncode != 0 and "unknown switch -q" in r.stderr
 
 
+def _write_bmp(path, img, top_down=False):
+    """8-bit palettised BMP, rows padded to 4 bytes; bottom-up unless top_down (negative height)."""
+    import struct
+    h, w = img.shape
+    stride = (w + 3) & ~3
+    rows = np.zeros((h, stride), np.uint8)
+    rows[:, :w] = img if top_down else img[::-1]
+    pal = b"".join(bytes((k, k, k, 0)) for k in range(256))
+    off = 14 + 40 + 1024
+    hdr = b"BM" + struct.pack("<IHHI", off + stride * h, 0, 0, off) + struct.pack("<IiiHHIIiiII", 40, w, -h if top_down else h, 1, 8, 0, stride * h, 2835, 2835, 256, 0)
+    open(path, "wb").write(hdr + pal + rows.tobytes())
+
+
+def test_batch_cli_pipeline_on_a_cpu_stub(tmp_path):
+    """csrc/nblic_batch_cli.c end to end WITHOUT a GPU: the CLI is linked against tests/stubs/cli_stub_backend.c (the batch
+    entry points answered by the parity oracle -- test infrastructure, the product links libnblic_b200.so) so that its own
+    logic runs here: PGM (with comments) and BMP (bottom-up, top-down, padded rows) readers, grouping (-b0: one file per
+    group, the three-stage thread pipeline over more groups than ring slots), writers, and the error exits."""
+    import subprocess
+    from cpu_codecs import Oracle
+    from nblic_image_compression_b200.synth import gen
+    exe = tmp_path / "nblic_batch_stub"
+    subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-std=gnu99", "-fwrapv", "-ffp-contract=off", "-o", str(exe),
+                    os.path.join(ROOT, "nblic_image_compression_b200", "csrc", "nblic_batch_cli.c"),
+                    os.path.join(ROOT, "tests", "stubs", "cli_stub_backend.c"), os.path.join(ROOT, "oracle", "nblic_oracle.c"), "-lpthread"], check=True)
+    orc = Oracle()
+    imgs = [gen(37 + 5 * k, 50 + 3 * k, k) for k in range(7)]  # widths 50..68: BMP rows with 0..3 bytes of padding
+    inputs = []
+    for k, im in enumerate(imgs):
+        path = tmp_path / f"in{k}.{'bmp' if k % 3 else 'pgm'}"
+        if k % 3 == 0:
+            path.write_bytes(b"P5\n# a comment\n%d %d\n255\n" % (im.shape[1], im.shape[0]) + im.tobytes())
+        else:
+            _write_bmp(path, im, top_down=k % 3 == 2)
+        inputs.append(path)
+    for switches, extra, near, effort in (("-cn0e0", ["-b0", "-v"], 0, 0), ("-cn2e1", [], 2, 1), ("-ce2", ["-b0"], 0, 2)):
+        out = tmp_path / ("enc" + switches[1:]); out.mkdir()
+        r = subprocess.run([str(exe), switches, *extra, str(out), *map(str, inputs)], check=True, capture_output=True, text=True)
+        if "-v" in extra:
+            assert "7 images in 7 groups" in r.stdout and "pipeline of read" in r.stdout, r.stdout
+        streams = []
+        for im, path in zip(imgs, inputs):
+            got = (out / (path.stem + ".nblic")).read_bytes()
+            exp, rec = (orc.q_encode(im), im) if effort == 0 else orc.n_encode(im, near, effort)[:2]
+            assert got == exp, (switches, path.name)
+            streams.append((out / (path.stem + ".nblic"), rec))
+        dec = tmp_path / ("dec" + switches[1:]); dec.mkdir()
+        subprocess.run([str(exe), "-d", *extra[:1], str(dec), *[str(p) for p, _ in streams]], check=True, stdout=subprocess.DEVNULL)
+        for path, rec in streams:
+            data = (dec / (path.stem + ".pgm")).read_bytes()
+            head = b"P5\n%d %d\n255\n" % (rec.shape[1], rec.shape[0])
+            assert data == head + rec.tobytes(), (switches, path.name)
+    bad = tmp_path / "noise.pgm"
+    bad.write_bytes(b"not an image at all")
+    r = subprocess.run([str(exe), "-c", str(tmp_path), str(inputs[0]), str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and "neither a binary PGM nor an 8-bit BMP" in r.stderr
+    r = subprocess.run([str(exe), "-c", str(tmp_path), str(tmp_path / "missing.pgm")], capture_output=True, text=True)
+    assert r.returncode != 0 and "open" in r.stderr
+    r = subprocess.run([str(exe), "-d", str(tmp_path), str(inputs[0])], capture_output=True, text=True)
+    assert r.returncode != 0 and "is not a .nblic stream" in r.stderr
+
+
 def test_header_is_plain_c(tmp_path):
     """include/nblic_b200.h must be consumable by a C99 compiler (the reference and its CLI are C)."""
     import subprocess
