@@ -1,9 +1,10 @@
 /*
  * tests/stubs/cli_stub_backend.c -- TEST INFRASTRUCTURE, never shipped: the handful of nblic_b200_* entry points that
- * csrc/nblic_batch_cli.c calls, implemented on the CPU by the parity oracle (oracle/nblic_oracle.c), so that the CLI's own
- * logic -- switch parsing, PGM / BMP readers, grouping by staging budget, the reader / coder / writer thread pipeline,
- * error paths -- runs under `pytest -m "not gpu"` in a container without a GPU.  The product never links this file:
- * nblic_batch proper links libnblic_b200.so, which has no CPU path.
+ * csrc/nblic_batch_cli.c and csrc/nblic_dropin.c call, implemented on the CPU by the parity oracle
+ * (oracle/nblic_oracle.c), so that the HOST-side C above the batch ABI -- the CLI's switch parsing, PGM / BMP readers,
+ * grouping, reader / coder / writer threads and error paths; the drop-in wrappers' header-before-validation, in-place
+ * clipping, reconstruction copy-back and extent probing -- runs under `pytest -m "not gpu"` in a container without a GPU.
+ * The product never links this file: nblic_batch and the drop-in symbols proper live on libnblic_b200.so, which has no CPU path.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -33,7 +34,7 @@ int nblic_b200_peek(const uint8_t *p, size_t len, int *h, int *w, int *near, int
 int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *images, const int *hs, const int *ws, int near, int effort,
                             uint8_t *const *outs, const size_t *caps, size_t *lens, uint8_t *const *recon, int *status) {
     int i, failed = 0;
-    (void)c; (void)recon;
+    (void)c;
     for (i = 0; i < n; i++) {
         const size_t px = (size_t)hs[i] * ws[i];
         uint8_t *tmp = (uint8_t *)malloc(px), *out = (uint8_t *)malloc(2 * px + 65536);
@@ -43,6 +44,7 @@ int nblic_b200_encode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *imag
         else len = oracle_n_encode(tmp, hs[i], ws[i], &n_, &e_, out);
         status[i] = len > 0 && (size_t)len <= caps[i] ? NBLIC_B200_OK : NBLIC_B200_OVERFLOW;
         if (status[i] == NBLIC_B200_OK) { memcpy(outs[i], out, (size_t)len); lens[i] = (size_t)len; } else { lens[i] = 0; failed++; }
+        if (status[i] == NBLIC_B200_OK && recon && recon[i] && n_ > 0) memcpy(recon[i], tmp, px); /* the oracle codes in place, like the reference */
         free(tmp); free(out);
     }
     return failed;
@@ -58,7 +60,10 @@ int nblic_b200_decode_batch(nblic_b200_ctx *c, int n, const uint8_t *const *stre
         if ((size_t)h * w > caps[i]) { status[i] = NBLIC_B200_OVERFLOW; failed++; continue; }
         if (effort == 0) rc = oracle_q_decode((const uint16_t *)streams[i], (long)(lens[i] / 2), images[i], &h, &w);
         else rc = oracle_n_decode(streams[i], (long)lens[i], images[i], &h, &w, &near, &effort);
-        hs[i] = h; ws[i] = w; nears[i] = near; efforts[i] = effort;
+        if (hs) hs[i] = h;
+        if (ws) ws[i] = w;
+        if (nears) nears[i] = near;
+        if (efforts) efforts[i] = effort;
         status[i] = rc == 0 ? NBLIC_B200_OK : NBLIC_B200_CORRUPT;
         failed += rc != 0;
     }

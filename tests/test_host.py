@@ -122,6 +122,68 @@ def test_batch_cli_pipeline_on_a_cpu_stub(tmp_path):
     assert r.returncode != 0 and "is not a .nblic stream" in r.stderr
 
 
+def test_dropin_wrappers_on_a_cpu_stub(tmp_path):
+    """csrc/nblic_dropin.c (the reference's five entry points) WITHOUT a GPU: built into a shared object with the stub
+    backend, called through ctypes, compared with the oracle: header emitted before validation, near / effort clipped in
+    place, near > 0 leaves the reconstruction in the image buffer, decode from an exact-size buffer without a length hint,
+    with a hint, foreign magics rejected without output."""
+    import ctypes as C
+    import subprocess
+    from cpu_codecs import Oracle
+    from nblic_image_compression_b200.synth import gen
+    so = tmp_path / "libdropin_stub.so"
+    subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-std=gnu99", "-fwrapv", "-ffp-contract=off", "-o", str(so),
+                    os.path.join(ROOT, "nblic_image_compression_b200", "csrc", "nblic_dropin.c"),
+                    os.path.join(ROOT, "tests", "stubs", "cli_stub_backend.c"), os.path.join(ROOT, "oracle", "nblic_oracle.c"), "-lpthread"], check=True)
+    lib = C.CDLL(str(so))
+    u8p, u16p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.POINTER(C.c_int)
+    lib.nblic_b200_hint_input_len.argtypes = [C.c_size_t]
+    orc = Oracle()
+    img = gen(45, 67, 5)
+    h, w = img.shape
+    for near_in, effort_in in ((0, 1), (2, 1), (1, 3), (17, 0), (3, 9)):  # the last two are clipped to (9, 1) and (3, 3)
+        work = img.copy()
+        out = np.zeros(2 * h * w + 8192, np.uint8)
+        n_, e_ = C.c_int(near_in), C.c_int(effort_in)
+        n = lib.NBLICcompress(0, out.ctypes.data_as(u8p), work.ctypes.data_as(u8p), h, w, C.byref(n_), C.byref(e_))
+        near, effort = min(max(near_in, 0), 9), min(max(effort_in, 1), 3)
+        assert (n_.value, e_.value) == (near, effort)
+        exp, rec, _, _ = orc.n_encode(img, near, effort)
+        assert n == len(exp) and bytes(out[:n]) == exp
+        assert np.array_equal(work, rec)  # near > 0: the reconstruction; lossless: untouched
+        for hint in (False, True):
+            exact = np.frombuffer(exp, np.uint8).copy()  # exactly the stream, nothing behind it
+            dec = np.zeros(h * w, np.uint8)
+            hh, ww, nn, ee = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            if hint:
+                lib.nblic_b200_hint_input_len(len(exp))
+            rc = lib.NBLICdecompress(0, exact.ctypes.data_as(u8p), dec.ctypes.data_as(u8p), C.byref(hh), C.byref(ww), C.byref(nn), C.byref(ee))
+            assert rc == 0 and (hh.value, ww.value, nn.value, ee.value) == (h, w, near, effort)
+            assert np.array_equal(dec.reshape(h, w), rec)
+    # the header is written before the dimensions are validated (NBLIC.c:768-775)
+    out = np.zeros(64, np.uint8)
+    n_, e_ = C.c_int(1), C.c_int(2)
+    assert lib.NBLICcompress(0, out.ctypes.data_as(u8p), img.ctypes.data_as(u8p), 0, 5, C.byref(n_), C.byref(e_)) == -1
+    assert bytes(out[:8]) == b"NBLIC0.3" and out[13] == 1 and out[15] == 2
+    # QNBLIC: words, the -t alias, sniffing
+    qexp = orc.q_encode(img)
+    for fn in (lib.QNBLICcompress, lib.QNBLICcompressMultiThread):
+        qout = np.zeros(h * w + 4096, np.uint16)
+        work = img.copy()
+        words = fn(qout.ctypes.data_as(u16p), work.ctypes.data_as(u8p), h, w)
+        assert words * 2 == len(qexp) and qout[:words].tobytes() == qexp and np.array_equal(work, img)
+    dec = np.zeros(h * w, np.uint8)
+    hh, ww = C.c_int(), C.c_int()
+    qbuf = np.frombuffer(qexp, np.uint16).copy()
+    assert lib.QNBLICdecompress(qbuf.ctypes.data_as(u16p), dec.ctypes.data_as(u8p), C.byref(hh), C.byref(ww)) == 0
+    assert (hh.value, ww.value) == (h, w) and np.array_equal(dec.reshape(h, w), img)
+    hh, ww = C.c_int(-7), C.c_int(-7)
+    nbuf = np.frombuffer(orc.n_encode(img, 0, 1)[0], np.uint8).copy()
+    assert lib.QNBLICdecompress(nbuf.ctypes.data_as(u16p), dec.ctypes.data_as(u8p), C.byref(hh), C.byref(ww)) == -1  # the CLI's format sniff (NBLIC_main.c:223)
+    assert (hh.value, ww.value) == (-7, -7)
+    assert lib.QNBLICcompress(qbuf.ctypes.data_as(u16p), img.ctypes.data_as(u8p), 0, 9) == -1
+
+
 def test_header_is_plain_c(tmp_path):
     """include/nblic_b200.h must be consumable by a C99 compiler (the reference and its CLI are C)."""
     import subprocess
